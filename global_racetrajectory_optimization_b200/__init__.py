@@ -1,0 +1,11 @@
+"""global_racetrajectory_optimization_b200 -- B200-native batched minimum-curvature / shortest-path QP path.
+
+``import global_racetrajectory_optimization_b200 as tph`` gives the call surface that
+/root/reference/main_globaltraj.py uses on its mincurv / mincurv_iqp / shortest_path branches
+(``tph.opt_min_curv.opt_min_curv(...)`` etc.); ``batch`` holds the batched device API.
+"""
+from . import (batch, calc_head_curv_an, calc_splines, create_raceline, iqp_handler,  # noqa: F401
+               opt_min_curv, opt_shortest_path, synth)
+from .spline_system import SplineSystem  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,350 @@
+"""Batched device API of the B200 minimum-curvature path.
+
+Thin host logic above the C-ABI (include/mincurv_b200.h): torch tensors are used only as device
+buffer holders (allocation, streams); every computation happens in the CUDA kernels of
+``libmincurv_b200.so``.  There is no CPU fallback -- without a CUDA device these functions raise.
+
+The batched entry points have no counterpart in the reference (which solves one track per call);
+the single-track modules next to this file (``opt_min_curv.py`` ...) mirror the tph call surface
+used by /root/reference/main_globaltraj.py:264-290,371-387 on top of them.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Union
+
+import torch
+
+from . import _lib
+
+N_MIN = 80          # smallest closed track the banded solver supports (csrc/common.cuh N_MIN)
+STATUS_TEXT = {
+    0: "ok",
+    1: "Problem not solvable, track might be too small to run with current safety distance!",
+    2: "interior-point iteration cap reached",
+    3: "numerical breakdown (non-positive pivot)",
+    4: "curvature constraint rows are active at the box-constrained optimum",
+    -1: "unsupported track size",
+}
+
+_WS = {}
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise _lib.MinCurvLibError("global_racetrajectory_optimization_b200 needs a CUDA device (B200, sm_100a); "
+                                   "there is no CPU fallback")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _workspace(kind: str, nbytes: int, device) -> torch.Tensor:
+    key = (kind, str(device))
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        _WS[key] = None
+        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws
+
+
+def release_workspaces() -> None:
+    _WS.clear()
+
+
+def _f64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor")
+    if t.dtype != torch.float64:
+        raise TypeError(f"{name} must be float64")
+    return t.contiguous()
+
+
+def _npts(n_pts, B, device):
+    if n_pts is None:
+        return None
+    n_pts = n_pts.to(device=device, dtype=torch.int32).contiguous()
+    if n_pts.numel() != B:
+        raise ValueError("n_pts must have one entry per track")
+    return n_pts
+
+
+# ------------------------------------------------------------------------------------------------
+def calc_splines_batch(xy: torch.Tensor, n_pts: Optional[torch.Tensor] = None,
+                       el_lengths: Optional[torch.Tensor] = None, use_dist_scaling: bool = True,
+                       want_coeffs: bool = True):
+    """Closed cubic splines through the points of every track.
+
+    xy: [B, n_max, 2] (or a reftrack [B, n_max, 4]); returns (coeffs_x, coeffs_y, normvec, h)."""
+    _require_cuda()
+    lib = _lib.load()
+    xy = _f64(xy, "xy")
+    B, n_max, stride = xy.shape
+    dev = xy.device
+    n_pts = _npts(n_pts, B, dev)
+    cx = torch.zeros((B, n_max, 4), dtype=torch.float64, device=dev) if want_coeffs else None
+    cy = torch.zeros((B, n_max, 4), dtype=torch.float64, device=dev) if want_coeffs else None
+    nv = torch.zeros((B, n_max, 2), dtype=torch.float64, device=dev)
+    h = torch.ones((B, n_max), dtype=torch.float64, device=dev)
+    if el_lengths is not None:
+        el_lengths = _f64(el_lengths, "el_lengths")
+    nbytes = lib.mc_calc_splines_workspace_bytes(B, n_max)
+    ws = _workspace("splines", nbytes, dev)
+    rc = lib.mc_calc_splines_batch(B, n_max, _ptr(n_pts), _ptr(xy), stride, _ptr(el_lengths), int(bool(use_dist_scaling)),
+                                   _ptr(cx), _ptr(cy), _ptr(nv), _ptr(h), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "mc_calc_splines_batch")
+    return cx, cy, nv, h
+
+
+def _wveh(w_veh, B, dev):
+    if isinstance(w_veh, torch.Tensor):
+        wb = w_veh.to(device=dev, dtype=torch.float64).contiguous()
+        if wb.numel() != B:
+            raise ValueError("w_veh tensor must have one entry per track")
+        return 0.0, wb
+    return float(w_veh), None
+
+
+def _chunk(B: int, per_item_bytes: int, device) -> int:
+    free, _ = torch.cuda.mem_get_info(device)
+    budget = max(int(free * 0.6), per_item_bytes)
+    return max(1, min(B, budget // max(per_item_bytes, 1)))
+
+
+def opt_min_curv_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, kappa_bound: float,
+                       w_veh: Union[float, torch.Tensor], n_pts: Optional[torch.Tensor] = None,
+                       max_chunk: Optional[int] = None) -> dict:
+    """Batched tph.opt_min_curv (closed tracks).  Returns a dict of device tensors:
+    alpha [B, n_max], curv_error_max [B], kappa_lin_max [B], status [B] (int32), iters [B] (int32)."""
+    _require_cuda()
+    lib = _lib.load()
+    reftrack = _f64(reftrack, "reftrack")
+    normvec = _f64(normvec, "normvec")
+    h = _f64(h, "h")
+    B, n_max, four = reftrack.shape
+    if four != 4 or normvec.shape != (B, n_max, 2) or h.shape != (B, n_max):
+        raise RuntimeError("Array size of reftrack should be the same as normvectors!")
+    if n_max < N_MIN:
+        raise NotImplementedError(f"closed tracks with fewer than {N_MIN} points are not supported by the banded solver")
+    dev = reftrack.device
+    n_pts = _npts(n_pts, B, dev)
+    w_scalar, w_batch = _wveh(w_veh, B, dev)
+    alpha = torch.empty((B, n_max), dtype=torch.float64, device=dev)
+    cerr = torch.empty((B,), dtype=torch.float64, device=dev)
+    kmax = torch.empty((B,), dtype=torch.float64, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    iters = torch.empty((B,), dtype=torch.int32, device=dev)
+    per_item = lib.mc_mincurv_workspace_bytes(1, n_max)
+    chunk = _chunk(B, per_item, dev) if max_chunk is None else min(B, max_chunk)
+    ws = _workspace("mincurv", lib.mc_mincurv_workspace_bytes(chunk, n_max), dev)
+    for s in range(0, B, chunk):
+        e = min(B, s + chunk)
+        rc = lib.mc_mincurv_solve_batch(e - s, n_max, _ptr(n_pts[s:e]) if n_pts is not None else None,
+                                        _ptr(reftrack[s:e]), _ptr(normvec[s:e]), _ptr(h[s:e]), float(kappa_bound),
+                                        w_scalar, _ptr(w_batch[s:e]) if w_batch is not None else None,
+                                        _ptr(alpha[s:e]), _ptr(cerr[s:e]), _ptr(kmax[s:e]), _ptr(status[s:e]),
+                                        _ptr(iters[s:e]), _ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, "mc_mincurv_solve_batch")
+    return dict(alpha=alpha, curv_error_max=cerr, kappa_lin_max=kmax, status=status, iters=iters)
+
+
+def opt_shortest_path_batch(reftrack: torch.Tensor, normvec: torch.Tensor, w_veh: Union[float, torch.Tensor],
+                            n_pts: Optional[torch.Tensor] = None) -> dict:
+    """Batched tph.opt_shortest_path.  Returns dict(alpha, status, iters)."""
+    _require_cuda()
+    lib = _lib.load()
+    reftrack = _f64(reftrack, "reftrack")
+    normvec = _f64(normvec, "normvec")
+    B, n_max, four = reftrack.shape
+    if four != 4 or normvec.shape != (B, n_max, 2):
+        raise RuntimeError("Array size of reftrack should be the same as normvectors!")
+    dev = reftrack.device
+    n_pts = _npts(n_pts, B, dev)
+    w_scalar, w_batch = _wveh(w_veh, B, dev)
+    alpha = torch.empty((B, n_max), dtype=torch.float64, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    iters = torch.empty((B,), dtype=torch.int32, device=dev)
+    ws = _workspace("shortest", lib.mc_shortest_path_workspace_bytes(B, n_max), dev)
+    rc = lib.mc_shortest_path_solve_batch(B, n_max, _ptr(n_pts), _ptr(reftrack), _ptr(normvec), w_scalar, _ptr(w_batch),
+                                          _ptr(alpha), _ptr(status), _ptr(iters), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "mc_shortest_path_solve_batch")
+    return dict(alpha=alpha, status=status, iters=iters)
+
+
+def create_raceline_batch(refline: torch.Tensor, normvec: torch.Tensor, alpha: torch.Tensor, stepsize_interp: float,
+                          n_pts: Optional[torch.Tensor] = None, n_out_max: Optional[int] = None,
+                          with_head_curv: bool = True) -> dict:
+    """Batched tph.create_raceline (+ tph.calc_head_curv_an at the resampled points).
+
+    refline: [B, n_max, 2] or a reftrack [B, n_max, 4].  If n_out_max is None an upper bound is derived from
+    the polygon length of the shifted line (one small device->host read)."""
+    _require_cuda()
+    lib = _lib.load()
+    refline = _f64(refline, "refline")
+    normvec = _f64(normvec, "normvec")
+    alpha = _f64(alpha, "alpha")
+    B, n_max, stride = refline.shape
+    dev = refline.device
+    n_pts = _npts(n_pts, B, dev)
+    if n_out_max is None:
+        pts = refline[:, :, :2] + alpha.unsqueeze(-1) * normvec
+        seg = (torch.roll(pts, -1, dims=1) - pts).norm(dim=-1)
+        if n_pts is not None:      # padded tail must not count (its closing segment is replaced below)
+            idx = torch.arange(n_max, device=dev).unsqueeze(0)
+            last = (n_pts.long() - 1).clamp(min=0).unsqueeze(1)
+            closing = (pts[:, 0, :] - torch.gather(pts, 1, last.unsqueeze(-1).expand(-1, 1, 2)).squeeze(1)).norm(dim=-1)
+            seg = torch.where(idx < last, seg, torch.zeros_like(seg))
+            poly = seg.sum(dim=1) + closing
+        else:
+            poly = seg.sum(dim=1)
+        n_out_max = int(math.ceil(float(poly.max().item()) * 1.1 / float(stepsize_interp))) + 16
+    n_out_max = int(n_out_max)
+    f64 = dict(dtype=torch.float64, device=dev)
+    out = dict(
+        coeffs_x=torch.zeros((B, n_max, 4), **f64), coeffs_y=torch.zeros((B, n_max, 4), **f64),
+        spline_lengths=torch.zeros((B, n_max), **f64), n_out=torch.zeros((B,), dtype=torch.int32, device=dev),
+        raceline_interp=torch.zeros((B, n_out_max, 2), **f64),
+        spline_inds=torch.zeros((B, n_out_max), dtype=torch.int32, device=dev),
+        t_values=torch.zeros((B, n_out_max), **f64), s_interp=torch.zeros((B, n_out_max), **f64),
+        el_lengths_interp=torch.zeros((B, n_out_max), **f64),
+        psi=torch.zeros((B, n_out_max), **f64) if with_head_curv else None,
+        kappa=torch.zeros((B, n_out_max), **f64) if with_head_curv else None,
+    )
+    ws = _workspace("splines", lib.mc_create_raceline_workspace_bytes(B, n_max), dev)
+    rc = lib.mc_create_raceline_batch(B, n_max, _ptr(n_pts), _ptr(refline), stride, _ptr(normvec), _ptr(alpha),
+                                      float(stepsize_interp), n_out_max, _ptr(out["coeffs_x"]), _ptr(out["coeffs_y"]),
+                                      _ptr(out["spline_lengths"]), _ptr(out["n_out"]), _ptr(out["raceline_interp"]),
+                                      _ptr(out["spline_inds"]), _ptr(out["t_values"]), _ptr(out["s_interp"]),
+                                      _ptr(out["el_lengths_interp"]), _ptr(out["psi"]), _ptr(out["kappa"]),
+                                      _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "mc_create_raceline_batch")
+    return out
+
+
+def calc_head_curv_batch(coeffs_x: torch.Tensor, coeffs_y: torch.Tensor, ind_spls: torch.Tensor, t_spls: torch.Tensor,
+                         n_eval: Optional[torch.Tensor] = None, calc_curv: bool = True, calc_dcurv: bool = False):
+    _require_cuda()
+    lib = _lib.load()
+    if not calc_curv and calc_dcurv:
+        raise ValueError("dkappa cannot be calculated without kappa!")
+    coeffs_x = _f64(coeffs_x, "coeffs_x")
+    coeffs_y = _f64(coeffs_y, "coeffs_y")
+    t_spls = _f64(t_spls, "t_spls")
+    B, n_max, _ = coeffs_x.shape
+    dev = coeffs_x.device
+    ind = ind_spls.to(device=dev, dtype=torch.int32).contiguous()
+    n_eval_max = t_spls.shape[1]
+    psi = torch.empty((B, n_eval_max), dtype=torch.float64, device=dev)
+    kappa = torch.empty_like(psi) if calc_curv else None
+    dkappa = torch.empty_like(psi) if calc_dcurv else None
+    rc = lib.mc_calc_head_curv_batch(B, n_max, _ptr(coeffs_x), _ptr(coeffs_y), n_eval_max,
+                                     _ptr(_npts(n_eval, B, dev)), _ptr(ind), _ptr(t_spls), _ptr(psi), _ptr(kappa),
+                                     _ptr(dkappa), _stream())
+    _lib.check(rc, "mc_calc_head_curv_batch")
+    return psi, kappa, dkappa
+
+
+def iqp_relinearise_batch(reftrack, normvec, alpha, stepsize_interp, n_pts=None, active=None, n_max_new=None):
+    """One re-linearisation step of tph.iqp_handler for every (active) track: returns
+    (reftrack_new [B, n_max_new, 4], normvec_new [B, n_max_new, 2], n_pts_new [B])."""
+    _require_cuda()
+    lib = _lib.load()
+    reftrack = _f64(reftrack, "reftrack")
+    normvec = _f64(normvec, "normvec")
+    alpha = _f64(alpha, "alpha")
+    B, n_max, _ = reftrack.shape
+    dev = reftrack.device
+    n_pts = _npts(n_pts, B, dev)
+    if n_max_new is None:
+        n_max_new = n_max + 64
+    if active is not None:
+        active = active.to(device=dev, dtype=torch.int32).contiguous()
+    rnew = torch.zeros((B, n_max_new, 4), dtype=torch.float64, device=dev)
+    nnew = torch.zeros((B, n_max_new, 2), dtype=torch.float64, device=dev)
+    npn = torch.zeros((B,), dtype=torch.int32, device=dev)
+    ws = _workspace("iqp", lib.mc_iqp_relinearise_workspace_bytes(B, n_max, n_max_new), dev)
+    rc = lib.mc_iqp_relinearise_batch(B, n_max, _ptr(n_pts), _ptr(active), _ptr(reftrack), _ptr(normvec), _ptr(alpha),
+                                      float(stepsize_interp), int(n_max_new), _ptr(rnew), _ptr(nnew), _ptr(npn),
+                                      _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "mc_iqp_relinearise_batch")
+    return rnew, nnew, npn
+
+
+def scale_alpha_batch(alpha: torch.Tensor, scale: Union[float, torch.Tensor]) -> None:
+    lib = _lib.load()
+    B, n_max = alpha.shape
+    sb = scale.to(device=alpha.device, dtype=torch.float64).contiguous() if isinstance(scale, torch.Tensor) else None
+    rc = lib.mc_scale_alpha_batch(B, n_max, _ptr(alpha), _ptr(sb), 1.0 if sb is not None else float(scale), _stream())
+    _lib.check(rc, "mc_scale_alpha_batch")
+
+
+def iqp_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, kappa_bound: float,
+              w_veh: Union[float, torch.Tensor], stepsize_interp: float, iters_min: int = 3,
+              curv_error_allowed: float = 0.01, n_pts: Optional[torch.Tensor] = None, max_iters: int = 50,
+              fixed_iters: Optional[int] = None) -> dict:
+    """Batched tph.iqp_handler: per-instance outer iterations with damping and
+    re-linearisation; an instance leaves the loop once iter >= iters_min and its curv_error_max <=
+    curv_error_allowed.  Returns dict(alpha [B, n_cap], reftrack [B, n_cap, 4], normvec [B, n_cap, 2],
+    n_pts [B], outer_iters [B], status [B], qp_solves) -- every array refers to the instance's LAST iteration.
+
+    fixed_iters: run exactly that many outer iterations for every instance (bench config C3)."""
+    _require_cuda()
+    reftrack = _f64(reftrack, "reftrack").clone()
+    normvec = _f64(normvec, "normvec").clone()
+    h = _f64(h, "h").clone()
+    B, n_max, _ = reftrack.shape
+    dev = reftrack.device
+    n_cap = n_max + 64
+    cur_n = (n_pts.to(device=dev, dtype=torch.int32).clone() if n_pts is not None
+             else torch.full((B,), n_max, dtype=torch.int32, device=dev))
+    fin = dict(alpha=torch.zeros((B, n_cap), dtype=torch.float64, device=dev),
+               reftrack=torch.zeros((B, n_cap, 4), dtype=torch.float64, device=dev),
+               normvec=torch.zeros((B, n_cap, 2), dtype=torch.float64, device=dev),
+               n_pts=torch.zeros((B,), dtype=torch.int32, device=dev),
+               outer_iters=torch.zeros((B,), dtype=torch.int32, device=dev),
+               status=torch.zeros((B,), dtype=torch.int32, device=dev),
+               curv_error_max=torch.zeros((B,), dtype=torch.float64, device=dev))
+    active = torch.ones((B,), dtype=torch.bool, device=dev)
+    qp_solves = 0
+    it = 0
+    limit = fixed_iters if fixed_iters is not None else max_iters
+    while True:
+        it += 1
+        n_cur_max = reftrack.shape[1]
+        res = opt_min_curv_batch(reftrack, normvec, h, kappa_bound, w_veh, n_pts=cur_n)
+        qp_solves += int(active.sum().item())
+        alpha = res["alpha"]
+        if it < iters_min:
+            scale_alpha_batch(alpha, it * 1.0 / iters_min)
+        failed = (res["status"] != 0) & (res["status"] != 4)
+        if fixed_iters is not None:
+            done = active & (torch.full_like(active, it >= fixed_iters) | failed)
+        else:
+            done = active & (((res["curv_error_max"] <= curv_error_allowed) & (it >= iters_min)) | failed | (it >= limit))
+        if bool(done.any().item()):
+            idx = done.nonzero(as_tuple=True)[0]
+            fin["alpha"][idx, :n_cur_max] = alpha[idx]
+            fin["reftrack"][idx, :n_cur_max] = reftrack[idx]
+            fin["normvec"][idx, :n_cur_max] = normvec[idx]
+            fin["n_pts"][idx] = cur_n[idx]
+            fin["outer_iters"][idx] = it
+            fin["status"][idx] = res["status"][idx]
+            fin["curv_error_max"][idx] = res["curv_error_max"][idx]
+        active = active & ~done
+        if not bool(active.any().item()):
+            break
+        reftrack, normvec, cur_n = iqp_relinearise_batch(reftrack, normvec, alpha, stepsize_interp, n_pts=cur_n,
+                                                         active=active, n_max_new=n_cap)
+        too_big = active & (cur_n < 0)
+        if bool(too_big.any().item()):
+            raise RuntimeError("iqp_batch: a re-sampled raceline needs more points than the padded capacity")
+        h = torch.ones((B, n_cap), dtype=torch.float64, device=dev)   # use_dist_scaling=False from iteration 2 on
+    fin["qp_solves"] = qp_solves
+    return fin

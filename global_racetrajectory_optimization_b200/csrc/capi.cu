@@ -1,0 +1,274 @@
+// extern "C" boundary of libmincurv_b200.so -- see include/mincurv_b200.h for the contract and the
+// reference call sites each entry point replaces.
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/mincurv_b200.h"
+#include "mincurv_ws.cuh"
+
+namespace mc {
+size_t spline_ws_doubles(int n_max);
+size_t pdip_smem_bytes();
+void launch_mincurv_setup(int, int, const int32_t *, const double *, const double *, const double *, double,
+                          const double *, double *, const Layout &, int32_t *, cudaStream_t);
+int launch_mincurv_pdip(int, int, const int32_t *, double *, const Layout &, const PdipParams &, double *, int32_t *,
+                        int32_t *, int, cudaStream_t);
+void launch_mincurv_finalize(int, int, const int32_t *, double *, const Layout &, const double *, double, double *,
+                             double *, int32_t *, cudaStream_t);
+void launch_calc_splines(int, int, const int32_t *, const double *, int, const double *, int, double *, double *,
+                         double *, double *, double *, cudaStream_t);
+void launch_create_raceline(int, int, const int32_t *, const double *, int, const double *, const double *, double, int,
+                            double *, double *, double *, int32_t *, double *, int32_t *, double *, double *, double *,
+                            double *, double *, double *, cudaStream_t);
+void launch_head_curv(int, int, const double *, const double *, int, const int32_t *, const int32_t *, const double *,
+                      double *, double *, double *, cudaStream_t);
+void launch_iqp_new_reftrack(int, int, const int32_t *, const int32_t *, const double *, const double *, const double *,
+                             int, const int32_t *, const double *, const int32_t *, const double *, double *, double *,
+                             int32_t *, cudaStream_t);
+void launch_scale_alpha(int, int, double *, const double *, double, cudaStream_t);
+size_t shortest_path_ws_doubles(int n_max);
+int launch_shortest_path(int, int, const int32_t *, const double *, const double *, double, const double *, double *,
+                         int32_t *, int32_t *, double *, cudaStream_t);
+}  // namespace mc
+
+static thread_local char g_err[256] = "";
+
+static int check_cuda(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        return MC_ECUDA;
+    }
+    return MC_OK;
+}
+static int bad(const char *msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return MC_EINVAL;
+}
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+extern "C" {
+
+int mc_version(void) { return 100; }
+const char *mc_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------------------
+size_t mc_calc_splines_workspace_bytes(int B, int n_max) {
+    if (B <= 0 || n_max <= 0) return 0;
+    return align256((size_t)B * mc::spline_ws_doubles(n_max) * sizeof(double));
+}
+
+int mc_calc_splines_batch(int B, int n_max, const int32_t *n_pts, const double *xy, int xy_stride,
+                          const double *el_lengths, int use_dist_scaling, double *coeffs_x, double *coeffs_y,
+                          double *normvec, double *h_out, void *workspace, size_t workspace_bytes, void *stream) {
+    if (B <= 0 || n_max < 3 || !xy || (xy_stride != 2 && xy_stride != 4)) return bad("mc_calc_splines_batch: bad argument");
+    if ((coeffs_x == nullptr) != (coeffs_y == nullptr)) return bad("mc_calc_splines_batch: coeffs_x/coeffs_y must both be given or both NULL");
+    if (!workspace || workspace_bytes < mc_calc_splines_workspace_bytes(B, n_max)) {
+        snprintf(g_err, sizeof(g_err), "mc_calc_splines_batch: workspace too small");
+        return MC_EWORKSPACE;
+    }
+    mc::launch_calc_splines(B, n_max, n_pts, xy, xy_stride, el_lengths, use_dist_scaling, coeffs_x, coeffs_y, normvec,
+                            h_out, (double *)workspace, (cudaStream_t)stream);
+    return check_cuda("mc_calc_splines_batch");
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t mc_mincurv_workspace_bytes(int B, int n_max) {
+    if (B <= 0 || n_max < mc::N_MIN) return 0;
+    const mc::Layout L = mc::make_layout(n_max);
+    return align256((size_t)B * L.stride * sizeof(double));
+}
+
+static int mincurv_args(const char *who, int B, int n_max, void *workspace, size_t workspace_bytes) {
+    if (B <= 0) return bad("mincurv: B <= 0");
+    if (n_max < mc::N_MIN) return bad("mincurv: n_max below the supported minimum (80 points)");
+    if (!workspace || workspace_bytes < mc_mincurv_workspace_bytes(B, n_max)) {
+        snprintf(g_err, sizeof(g_err), "%s: workspace too small", who);
+        return MC_EWORKSPACE;
+    }
+    return MC_OK;
+}
+
+int mc_mincurv_setup_batch(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
+                           const double *h, double w_veh, const double *w_veh_batch, int32_t *status, void *workspace,
+                           size_t workspace_bytes, void *stream) {
+    if (!reftrack || !normvec || !h || !status) return bad("mc_mincurv_setup_batch: NULL argument");
+    int rc = mincurv_args("mc_mincurv_setup_batch", B, n_max, workspace, workspace_bytes);
+    if (rc) return rc;
+    mc::launch_mincurv_setup(B, n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, (double *)workspace,
+                             mc::make_layout(n_max), status, (cudaStream_t)stream);
+    return check_cuda("mincurv_setup_kernel");
+}
+
+int mc_mincurv_pdip_batch(int B, int n_max, const int32_t *n_pts, double *alpha, int32_t *status, int32_t *iters,
+                          void *workspace, size_t workspace_bytes, void *stream) {
+    if (!alpha || !status) return bad("mc_mincurv_pdip_batch: NULL argument");
+    int rc = mincurv_args("mc_mincurv_pdip_batch", B, n_max, workspace, workspace_bytes);
+    if (rc) return rc;
+    mc::PdipParams prm;
+    prm.max_iter = 40;
+    prm.mu_rel = 1e-11;
+    prm.rd_rel = 1e-9;
+    prm.eta = 0.995;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int per_sm = (int)((227 * 1024) / mc::pdip_smem_bytes());
+    int grid = sms * (per_sm > 0 ? per_sm : 1);
+    if (grid > B) grid = B;
+    if (mc::launch_mincurv_pdip(B, n_max, n_pts, (double *)workspace, mc::make_layout(n_max), prm, alpha, status, iters,
+                                grid, (cudaStream_t)stream) != 0) {
+        snprintf(g_err, sizeof(g_err), "mincurv_pdip_kernel: cudaFuncSetAttribute failed");
+        return MC_ECUDA;
+    }
+    return check_cuda("mincurv_pdip_kernel");
+}
+
+int mc_mincurv_finalize_batch(int B, int n_max, const int32_t *n_pts, const double *alpha, double kappa_bound,
+                              double *curv_error_max, double *kappa_lin_max, int32_t *status, void *workspace,
+                              size_t workspace_bytes, void *stream) {
+    if (!alpha || !curv_error_max || !status) return bad("mc_mincurv_finalize_batch: NULL argument");
+    int rc = mincurv_args("mc_mincurv_finalize_batch", B, n_max, workspace, workspace_bytes);
+    if (rc) return rc;
+    mc::launch_mincurv_finalize(B, n_max, n_pts, (double *)workspace, mc::make_layout(n_max), alpha, kappa_bound,
+                                curv_error_max, kappa_lin_max, status, (cudaStream_t)stream);
+    return check_cuda("mincurv_finalize_kernel");
+}
+
+int mc_mincurv_solve_batch(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
+                           const double *h, double kappa_bound, double w_veh, const double *w_veh_batch, double *alpha,
+                           double *curv_error_max, double *kappa_lin_max, int32_t *status, int32_t *iters,
+                           void *workspace, size_t workspace_bytes, void *stream) {
+    if (!reftrack || !normvec || !h || !alpha || !curv_error_max || !status)
+        return bad("mc_mincurv_solve_batch: NULL argument");
+    int rc = mc_mincurv_setup_batch(B, n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, status, workspace,
+                                    workspace_bytes, stream);
+    if (rc) return rc;
+    rc = mc_mincurv_pdip_batch(B, n_max, n_pts, alpha, status, iters, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    return mc_mincurv_finalize_batch(B, n_max, n_pts, alpha, kappa_bound, curv_error_max, kappa_lin_max, status,
+                                     workspace, workspace_bytes, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t mc_shortest_path_workspace_bytes(int B, int n_max) {
+    if (B <= 0 || n_max < 3) return 0;
+    return align256((size_t)B * mc::shortest_path_ws_doubles(n_max) * sizeof(double));
+}
+
+int mc_shortest_path_solve_batch(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
+                                 double w_veh, const double *w_veh_batch, double *alpha, int32_t *status, int32_t *iters,
+                                 void *workspace, size_t workspace_bytes, void *stream) {
+    if (B <= 0 || n_max < 3 || !reftrack || !normvec || !alpha || !status)
+        return bad("mc_shortest_path_solve_batch: bad argument");
+    if (!workspace || workspace_bytes < mc_shortest_path_workspace_bytes(B, n_max)) {
+        snprintf(g_err, sizeof(g_err), "mc_shortest_path_solve_batch: workspace too small");
+        return MC_EWORKSPACE;
+    }
+    if (mc::launch_shortest_path(B, n_max, n_pts, reftrack, normvec, w_veh, w_veh_batch, alpha, status, iters,
+                                 (double *)workspace, (cudaStream_t)stream) != 0) {
+        snprintf(g_err, sizeof(g_err), "shortest_path_kernel: launch configuration failed");
+        return MC_ECUDA;
+    }
+    return check_cuda("shortest_path_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t mc_create_raceline_workspace_bytes(int B, int n_max) { return mc_calc_splines_workspace_bytes(B, n_max); }
+
+int mc_create_raceline_batch(int B, int n_max, const int32_t *n_pts, const double *refline, int ref_stride,
+                             const double *normvec, const double *alpha, double stepsize_interp, int n_out_max,
+                             double *coeffs_x, double *coeffs_y, double *spline_lengths, int32_t *n_out,
+                             double *raceline_interp, int32_t *spline_inds, double *t_values, double *s_interp,
+                             double *el_lengths_interp, double *psi, double *kappa, void *workspace,
+                             size_t workspace_bytes, void *stream) {
+    if (B <= 0 || n_max < 3 || n_out_max <= 0 || !refline || (ref_stride != 2 && ref_stride != 4) || !normvec || !alpha ||
+        !(stepsize_interp > 0.0) || !coeffs_x || !coeffs_y || !spline_lengths || !n_out || !raceline_interp ||
+        !spline_inds || !t_values || !s_interp || !el_lengths_interp)
+        return bad("mc_create_raceline_batch: bad argument");
+    if (!workspace || workspace_bytes < mc_create_raceline_workspace_bytes(B, n_max)) {
+        snprintf(g_err, sizeof(g_err), "mc_create_raceline_batch: workspace too small");
+        return MC_EWORKSPACE;
+    }
+    mc::launch_create_raceline(B, n_max, n_pts, refline, ref_stride, normvec, alpha, stepsize_interp, n_out_max,
+                               coeffs_x, coeffs_y, spline_lengths, n_out, raceline_interp, spline_inds, t_values,
+                               s_interp, el_lengths_interp, psi, kappa, (double *)workspace, (cudaStream_t)stream);
+    return check_cuda("create_raceline_kernel");
+}
+
+int mc_calc_head_curv_batch(int B, int n_max, const double *coeffs_x, const double *coeffs_y, int n_eval_max,
+                            const int32_t *n_eval, const int32_t *ind_spls, const double *t_spls, double *psi,
+                            double *kappa, double *dkappa, void *stream) {
+    if (B <= 0 || n_max <= 0 || n_eval_max <= 0 || !coeffs_x || !coeffs_y || !ind_spls || !t_spls || !psi)
+        return bad("mc_calc_head_curv_batch: bad argument");
+    if (dkappa && !kappa) return bad("dkappa cannot be calculated without kappa!");
+    mc::launch_head_curv(B, n_max, coeffs_x, coeffs_y, n_eval_max, n_eval, ind_spls, t_spls, psi, kappa, dkappa,
+                         (cudaStream_t)stream);
+    return check_cuda("head_curv_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace of the IQP re-linearisation: spline scratch + the create_raceline outputs it discards
+static size_t iqp_ws_parts(int B, int n_max, int n_max_new, size_t off[10]) {
+    size_t o = 0;
+    const size_t spl = align256((size_t)B * mc::spline_ws_doubles(n_max > n_max_new ? n_max : n_max_new) * sizeof(double));
+    off[0] = o; o += spl;                                                    // spline scratch
+    off[1] = o; o += align256((size_t)B * n_max * 4 * sizeof(double));       // coeffs_x
+    off[2] = o; o += align256((size_t)B * n_max * 4 * sizeof(double));       // coeffs_y
+    off[3] = o; o += align256((size_t)B * n_max * sizeof(double));           // spline_lengths
+    off[4] = o; o += align256((size_t)B * sizeof(int32_t));                  // n_out
+    off[5] = o; o += align256((size_t)B * n_max_new * 2 * sizeof(double));   // raceline_interp
+    off[6] = o; o += align256((size_t)B * n_max_new * sizeof(int32_t));      // spline_inds
+    off[7] = o; o += align256((size_t)B * n_max_new * sizeof(double));       // t_values
+    off[8] = o; o += align256((size_t)B * n_max_new * sizeof(double));       // s_interp
+    off[9] = o; o += align256((size_t)B * n_max_new * sizeof(double));       // el_lengths
+    return o;
+}
+
+size_t mc_iqp_relinearise_workspace_bytes(int B, int n_max, int n_max_new) {
+    if (B <= 0 || n_max < 3 || n_max_new < 3) return 0;
+    size_t off[10];
+    return iqp_ws_parts(B, n_max, n_max_new, off);
+}
+
+int mc_iqp_relinearise_batch(int B, int n_max, const int32_t *n_pts, const int32_t *active, const double *reftrack,
+                             const double *normvec, const double *alpha, double stepsize_interp, int n_max_new,
+                             double *reftrack_new, double *normvec_new, int32_t *n_pts_new, void *workspace,
+                             size_t workspace_bytes, void *stream) {
+    if (B <= 0 || n_max < 3 || n_max_new < 3 || !reftrack || !normvec || !alpha || !(stepsize_interp > 0.0) ||
+        !reftrack_new || !normvec_new || !n_pts_new)
+        return bad("mc_iqp_relinearise_batch: bad argument");
+    size_t off[10];
+    const size_t need = iqp_ws_parts(B, n_max, n_max_new, off);
+    if (!workspace || workspace_bytes < need) {
+        snprintf(g_err, sizeof(g_err), "mc_iqp_relinearise_batch: workspace too small");
+        return MC_EWORKSPACE;
+    }
+    char *w = (char *)workspace;
+    cudaStream_t s = (cudaStream_t)stream;
+    double *spl = (double *)(w + off[0]);
+    int32_t *n_out = (int32_t *)(w + off[4]);
+    mc::launch_create_raceline(B, n_max, n_pts, reftrack, 4, normvec, alpha, stepsize_interp, n_max_new,
+                               (double *)(w + off[1]), (double *)(w + off[2]), (double *)(w + off[3]), n_out,
+                               (double *)(w + off[5]), (int32_t *)(w + off[6]), (double *)(w + off[7]),
+                               (double *)(w + off[8]), (double *)(w + off[9]), nullptr, nullptr, spl, s);
+    int rc = check_cuda("create_raceline_kernel");
+    if (rc) return rc;
+    mc::launch_iqp_new_reftrack(B, n_max, n_pts, active, reftrack, normvec, alpha, n_max_new, n_out,
+                                (double *)(w + off[5]), (int32_t *)(w + off[6]), (double *)(w + off[7]), reftrack_new,
+                                normvec_new, n_pts_new, s);
+    rc = check_cuda("iqp_new_reftrack_kernel");
+    if (rc) return rc;
+    // splines of the new reference line without distance scaling -> new normal vectors
+    mc::launch_calc_splines(B, n_max_new, n_pts_new, reftrack_new, 4, nullptr, 0, nullptr, nullptr, normvec_new, nullptr,
+                            spl, s);
+    return check_cuda("calc_splines_kernel");
+}
+
+int mc_scale_alpha_batch(int B, int n_max, double *alpha, const double *scale_batch, double scale, void *stream) {
+    if (B <= 0 || n_max <= 0 || !alpha) return bad("mc_scale_alpha_batch: bad argument");
+    mc::launch_scale_alpha(B, n_max, alpha, scale_batch, scale, (cudaStream_t)stream);
+    return check_cuda("scale_alpha_kernel");
+}
+
+}  // extern "C"

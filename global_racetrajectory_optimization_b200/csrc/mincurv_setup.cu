@@ -1,0 +1,180 @@
+// K2a -- assembly of the minimum-curvature QP in banded form (replaces the dense 4N x 4N inverse and
+// the ~10 dense GEMMs of tph.opt_min_curv, call site /root/reference/main_globaltraj.py:264-271).
+//
+// With the spline moments m = Tri^{-1} 6 D2 p (Tri cyclic tridiagonal, common.cuh) the quantities of
+// SURVEY.md A.2/A.3 become O(N) or banded:
+//   x', y'       = a1 coefficients of the reference spline          (A_ex_b A^{-1} q)
+//   T_c q        = h^2 m                                            (A_ex_c A^{-1} q)
+//   T_n{x,y} a   = h^2 Tri^{-1} 6 D2 (n_{x,y} a)   =>  E = S_y Z N_y - S_x Z N_x,  Z = Tri^{-1} 6 D2
+//   H = E^T E (half-bandwidth 32 kept),  f = F_SCALE E^T k_ref,  k_ref = S_y m_y - S_x m_x
+// One CTA per QP instance; O(N) vectors and the Z / H bands live in the instance's HBM slab.
+#include "mincurv_ws.cuh"
+
+namespace mc {
+
+// band of Z: ZB[m][BZ + o] = Z[m][m + o], o in [-BZ, BZ]; Z[m][i] = 6 (Ti[m][i-1]/h_{i-1}
+//   - Ti[m][i] (1/h_{i-1} + 1/h_i) + Ti[m][i+1]/h_i) with Ti = Tri^{-1} generated outwards from the
+// diagonal by the decay ratios rho+ / rho- (Ti is symmetric: Ti[m][m+o] = Ti[m+o][m]).
+__device__ inline void build_zband(double *zb, const double *h, const double *tii, const double *rhop,
+                                   const double *rhom, int n) {
+    for (int m = threadIdx.x; m < n; m += blockDim.x) {
+        double *row = zb + (size_t)m * ZB_PITCH;
+        const double t0 = tii[m];
+        const int mm1 = (m == 0) ? n - 1 : m - 1;
+        const int mp1 = (m + 1 == n) ? 0 : m + 1;
+        const double tm1 = t0 * rhom[mm1];      // Ti[m][m-1]
+        const double tp1 = t0 * rhop[mp1];      // Ti[m][m+1]
+        {   // o = 0
+            const double him = h[mm1], hi = h[m];
+            row[BZ] = 6.0 * (tm1 / him - t0 * (1.0 / him + 1.0 / hi) + tp1 / hi);
+        }
+        // positive side: i = m + o
+        double tprev = t0, tcur = tp1;
+        int i = mp1;
+        for (int o = 1; o <= BZ; ++o) {
+            const int ip1 = (i + 1 == n) ? 0 : i + 1;
+            const int im1 = (i == 0) ? n - 1 : i - 1;
+            const double tnext = tcur * rhop[ip1];
+            const double him = h[im1], hi = h[i];
+            row[BZ + o] = 6.0 * (tprev / him - tcur * (1.0 / him + 1.0 / hi) + tnext / hi);
+            tprev = tcur; tcur = tnext; i = ip1;
+        }
+        // negative side: i = m - o
+        double tnx = t0;
+        tcur = tm1;
+        i = mm1;
+        for (int o = 1; o <= BZ; ++o) {
+            const int im1 = (i == 0) ? n - 1 : i - 1;
+            const double tpv = tcur * rhom[im1];          // Ti[m][i-1]
+            const double him = h[im1], hi = h[i];
+            row[BZ - o] = 6.0 * (tpv / him - tcur * (1.0 / him + 1.0 / hi) + tnx / hi);
+            tnx = tcur; tcur = tpv; i = im1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
+                     const double *__restrict__ reftrack, const double *__restrict__ normvec,
+                     const double *__restrict__ hin, double w_veh, const double *__restrict__ w_veh_batch,
+                     double *__restrict__ ws, Layout L, int32_t *__restrict__ status) {
+    const int b = blockIdx.x;
+    const int n = n_pts ? n_pts[b] : n_max;
+    double *slab = ws + (size_t)b * L.stride;
+    __shared__ int s_flag;
+    if (threadIdx.x == 0) s_flag = 0;
+    __syncthreads();
+    if (n < N_MIN || n > n_max) {
+        if (threadIdx.x == 0) status[b] = -1;   // unsupported size (see N_MIN)
+        return;
+    }
+    const double wv = w_veh_batch ? w_veh_batch[b] : w_veh;
+    const double *rt = reftrack + (size_t)b * n_max * 4;
+    const double *nv = normvec + (size_t)b * n_max * 2;
+    const double *hb = hin + (size_t)b * n_max;
+
+    double *H = vec(slab, L, V_H), *DG = vec(slab, L, V_DIAG), *DFW = vec(slab, L, V_DFW), *DBW = vec(slab, L, V_DBW);
+    double *LFW = vec(slab, L, V_LFW), *INVD = vec(slab, L, V_INVD), *TII = vec(slab, L, V_TII);
+    double *RHOP = vec(slab, L, V_RHOP), *RHOM = vec(slab, L, V_RHOM);
+    double *PX = vec(slab, L, V_PX), *PY = vec(slab, L, V_PY), *NX = vec(slab, L, V_NX), *NY = vec(slab, L, V_NY);
+    double *MX = vec(slab, L, V_MX), *MY = vec(slab, L, V_MY), *XP = vec(slab, L, V_XP), *YP = vec(slab, L, V_YP);
+    double *SX = vec(slab, L, V_SX), *SY = vec(slab, L, V_SY), *KREF = vec(slab, L, V_KREF);
+    double *LB = vec(slab, L, V_LB), *UB = vec(slab, L, V_UB), *F = vec(slab, L, V_F);
+    double *T0 = vec(slab, L, V_T0), *T1 = vec(slab, L, V_T1), *T2 = vec(slab, L, V_T2), *T3 = vec(slab, L, V_T3);
+
+    // ---- P1: coalesced, vectorised load of the reftrack rows [x, y, w_r, w_l] (32 B per point) ----
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double2 xy = *reinterpret_cast<const double2 *>(rt + (size_t)i * 4);
+        const double2 ww = *reinterpret_cast<const double2 *>(rt + (size_t)i * 4 + 2);
+        const double2 nn = *reinterpret_cast<const double2 *>(nv + (size_t)i * 2);
+        const int im1 = (i == 0) ? n - 1 : i - 1;
+        const double hi = hb[i], him = hb[im1];
+        PX[i] = xy.x; PY[i] = xy.y; NX[i] = nn.x; NY[i] = nn.y;
+        H[i] = hi;
+        DG[i] = 2.0 * (him + hi);
+        double ub = ww.x - 0.5 * wv;          // dev_max_right
+        double lb = -(ww.y - 0.5 * wv);       // -dev_max_left
+        if (lb > ub) s_flag = 1;              // tph: "Problem not solvable, track might be too small ..."
+        if (ub - lb < 2.0 * FIX_EPS) { const double mid = 0.5 * (lb + ub); lb = mid - FIX_EPS; ub = mid + FIX_EPS; }
+        LB[i] = lb; UB[i] = ub;
+    }
+    __syncthreads();
+    if (s_flag) {
+        if (threadIdx.x == 0) status[b] = 1;
+        return;
+    }
+    // ---- P2/P3: periodic LDL^T of the spline system, decay ratios of its inverse ----
+    tri_pivots(DG, H, DFW, DBW, n);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int im1 = (i == 0) ? n - 1 : i - 1;
+        const int ip1 = (i + 1 == n) ? 0 : i + 1;
+        const double hi = H[i], him = H[im1];
+        LFW[i] = him / DFW[im1];
+        INVD[i] = 1.0 / DFW[i];
+        TII[i] = 1.0 / (DFW[i] + DBW[i] - DG[i]);
+        RHOP[i] = -him / DBW[i];
+        RHOM[i] = -hi / DFW[i];
+        T0[i] = 6.0 * ((PX[ip1] - PX[i]) / hi - (PX[i] - PX[im1]) / him);
+        T1[i] = 6.0 * ((PY[ip1] - PY[i]) / hi - (PY[i] - PY[im1]) / him);
+    }
+    __syncthreads();
+    // ---- P4: moments of the reference line ----
+    tri_solve2(LFW, INVD, H, T0, T1, T2, T3, MX, MY, n);
+    // ---- P5: linearisation point ----
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ip1 = (i + 1 == n) ? 0 : i + 1;
+        const double hi = H[i], h2 = hi * hi;
+        const double xp = (PX[ip1] - PX[i]) - h2 * (2.0 * MX[i] + MX[ip1]) * (1.0 / 6.0);
+        const double yp = (PY[ip1] - PY[i]) - h2 * (2.0 * MY[i] + MY[ip1]) * (1.0 / 6.0);
+        const double q = xp * xp + yp * yp;
+        const double c = 1.0 / (q * sqrt(q));
+        const double sy = c * xp * h2, sx = c * yp * h2;
+        XP[i] = xp; YP[i] = yp; SX[i] = sx; SY[i] = sy;
+        KREF[i] = sy * MY[i] - sx * MX[i];
+    }
+    // ---- P6: band of Z ----
+    double *ZB = slab + L.o_zb;
+    build_zband(ZB, H, TII, RHOP, RHOM, n);
+    __syncthreads();
+    // ---- P7: f = F_SCALE E^T k_ref ----
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double nyi = NY[i], nxi = NX[i];
+        double acc = 0.0;
+        int m = wrapi(i - BZ, n);
+        for (int o = BZ; o >= -BZ; --o) {       // m = i - o
+            const double z = ZB[(size_t)m * ZB_PITCH + BZ + o];
+            acc += z * (SY[m] * nyi - SX[m] * nxi) * KREF[m];
+            m = (m + 1 == n) ? 0 : m + 1;
+        }
+        F[i] = F_SCALE * acc;
+    }
+    // ---- P8: band of H = E^T E: HB[i][k] = sum_m E[m][i] E[m][i+k], k = 0..32 ----
+    double *HB = slab + L.o_hb;
+    const int tot = n * (HBW + 1);
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+        const int i = e / (HBW + 1), k = e - i * (HBW + 1);
+        int j = i + k; if (j >= n) j -= n;
+        const double nyi = NY[i], nxi = NX[i], nyj = NY[j], nxj = NX[j];
+        // rows m with |m - i| <= BZ and |m - j| <= BZ:  m = i + k - BZ .. i + BZ
+        double acc = 0.0;
+        int m = wrapi(i + k - BZ, n);
+        for (int t = k - BZ; t <= BZ; ++t) {    // m = i + t ; column offsets: i - m = -t, j - m = k - t
+            const double *zr = ZB + (size_t)m * ZB_PITCH + BZ;
+            const double sy = SY[m], sx = SX[m];
+            acc += (zr[-t] * (sy * nyi - sx * nxi)) * (zr[k - t] * (sy * nyj - sx * nxj));
+            m = (m + 1 == n) ? 0 : m + 1;
+        }
+        HB[(size_t)i * HB_PITCH + k] = acc;
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) HB[(size_t)i * HB_PITCH + HBW + 1] = 0.0;
+    if (threadIdx.x == 0) status[b] = 0;
+}
+
+void launch_mincurv_setup(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
+                          const double *h, double w_veh, const double *w_veh_batch, double *ws, const Layout &L,
+                          int32_t *status, cudaStream_t stream) {
+    mincurv_setup_kernel<<<B, 256, 0, stream>>>(n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, ws, L, status);
+}
+
+}  // namespace mc

@@ -1,0 +1,153 @@
+"""Single-track call surface of the hot path, mirroring trajectory_planning_helpers 0.76 as used by
+/root/reference/main_globaltraj.py (keyword names, defaults, return arities, exception types):
+
+    calc_splines       prep_track.py:48-51, main_globaltraj.py:568
+    opt_min_curv       main_globaltraj.py:264-271, :344-350
+    iqp_handler        main_globaltraj.py:273-284
+    opt_shortest_path  main_globaltraj.py:286-290
+    create_raceline    main_globaltraj.py:371-376
+    calc_head_curv_an  main_globaltraj.py:383-387
+
+numpy in / numpy out; every call runs the CUDA kernels through the C-ABI with a batch of one
+(no CPU fallback: without the extension or a GPU these functions raise)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import batch as _b
+from .spline_system import SplineSystem, h_from_system
+
+
+def _dev():
+    _b._require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _up(a, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(_dev()).unsqueeze(0)
+
+
+def _raise_status(st: int):
+    if st == 0 or st == 4:
+        return
+    if st == 1:
+        raise RuntimeError(_b.STATUS_TEXT[1])
+    if st == 3:
+        raise ValueError("matrix G is not positive definite")
+    if st == 2:
+        raise RuntimeError("interior-point iteration cap reached without convergence")
+    raise NotImplementedError(_b.STATUS_TEXT.get(st, f"solver status {st}"))
+
+
+# ------------------------------------------------------------------------------------------------
+def calc_splines(path: np.ndarray, el_lengths: np.ndarray = None, psi_s: float = None, psi_e: float = None,
+                 use_dist_scaling: bool = True) -> tuple:
+    """tph.calc_splines.calc_splines -> (coeffs_x, coeffs_y, M, normvec_normalized).
+    ``M`` is a SplineSystem (lazy stand-in of the dense 4N x 4N matrix)."""
+    path = np.asarray(path, dtype=np.float64)
+    closed = bool(np.all(np.isclose(path[0], path[-1])) and psi_s is None)
+    if not closed and (psi_s is None or psi_e is None):
+        raise RuntimeError("Headings must be provided for unclosed spline calculation!")
+    if el_lengths is not None and path.shape[0] != el_lengths.size + 1:
+        raise RuntimeError("el_lengths input must be one element smaller than path input!")
+    if not closed:
+        raise NotImplementedError("open-path splines (psi_s/psi_e) are outside the B200 hot path; "
+                                  "main_globaltraj.py only ever passes closed paths")
+    pts = path[:-1, :2]
+    el = _up(el_lengths) if (el_lengths is not None and use_dist_scaling) else None
+    cx, cy, nv, h = _b.calc_splines_batch(_up(pts), el_lengths=el, use_dist_scaling=use_dist_scaling)
+    return (cx[0].cpu().numpy(), cy[0].cpu().numpy(), SplineSystem(h[0].cpu().numpy()), nv[0].cpu().numpy())
+
+
+def opt_min_curv(reftrack: np.ndarray, normvectors: np.ndarray, A, kappa_bound: float, w_veh: float,
+                 print_debug: bool = False, plot_debug: bool = False, closed: bool = True, psi_s: float = None,
+                 psi_e: float = None, fix_s: bool = False, fix_e: bool = False) -> tuple:
+    """tph.opt_min_curv.opt_min_curv -> (alpha_mincurv, curv_error_max)."""
+    reftrack = np.asarray(reftrack, dtype=np.float64)
+    normvectors = np.asarray(normvectors, dtype=np.float64)
+    no_points = reftrack.shape[0]
+    if no_points != normvectors.shape[0]:
+        raise RuntimeError("Array size of reftrack should be the same as normvectors!")
+    if not closed:
+        raise NotImplementedError("open tracks (closed=False) are outside the B200 hot path")
+    h = h_from_system(A, no_points)
+    res = _b.opt_min_curv_batch(_up(reftrack), _up(normvectors), _up(h), kappa_bound, float(w_veh))
+    st = int(res["status"][0].item())
+    _raise_status(st)
+    if st == 4:
+        raise NotImplementedError("the curvature constraint |kappa| <= kappa_bound is active for this track: "
+                                  "the curvature-row phase of the solver is not implemented yet "
+                                  f"(max linearised |kappa| = {float(res['kappa_lin_max'][0]):.4f})")
+    alpha = res["alpha"][0].cpu().numpy()
+    if print_debug:
+        print("IPM iterations opt_min_curv: %i" % int(res["iters"][0].item()))
+    return alpha, float(res["curv_error_max"][0].item())
+
+
+def opt_shortest_path(reftrack: np.ndarray, normvectors: np.ndarray, w_veh: float, print_debug: bool = False) -> np.ndarray:
+    """tph.opt_shortest_path.opt_shortest_path -> alpha_shpath."""
+    reftrack = np.asarray(reftrack, dtype=np.float64)
+    normvectors = np.asarray(normvectors, dtype=np.float64)
+    if reftrack.shape[0] != normvectors.shape[0]:
+        raise RuntimeError("Array size of reftrack should be the same as normvectors!")
+    res = _b.opt_shortest_path_batch(_up(reftrack), _up(normvectors), float(w_veh))
+    _raise_status(int(res["status"][0].item()))
+    return res["alpha"][0].cpu().numpy()
+
+
+def create_raceline(refline: np.ndarray, normvectors: np.ndarray, alpha: np.ndarray, stepsize_interp: float) -> tuple:
+    """tph.create_raceline.create_raceline -> 9-tuple (raceline_interp, A_raceline, coeffs_x_raceline,
+    coeffs_y_raceline, spline_inds_raceline_interp, t_values_raceline_interp, s_raceline_interp,
+    spline_lengths_raceline, el_lengths_raceline_interp_cl)."""
+    refline = np.asarray(refline, dtype=np.float64)
+    n = refline.shape[0]
+    out = _b.create_raceline_batch(_up(refline[:, :2]), _up(normvectors), _up(alpha), float(stepsize_interp),
+                                   with_head_curv=False)
+    no = int(out["n_out"][0].item())
+    if no <= 0:
+        raise RuntimeError("create_raceline: resampling buffer too small")
+    g = lambda k, m: out[k][0, :m].cpu().numpy()
+    return (g("raceline_interp", no), SplineSystem(np.ones(n)), g("coeffs_x", n), g("coeffs_y", n),
+            g("spline_inds", no).astype(int), g("t_values", no), g("s_interp", no), g("spline_lengths", n),
+            g("el_lengths_interp", no))
+
+
+def calc_head_curv_an(coeffs_x: np.ndarray, coeffs_y: np.ndarray, ind_spls: np.ndarray, t_spls: np.ndarray,
+                      calc_curv: bool = True, calc_dcurv: bool = False) -> tuple:
+    """tph.calc_head_curv_an.calc_head_curv_an -> (psi, kappa[, dkappa])."""
+    coeffs_x = np.asarray(coeffs_x, dtype=np.float64)
+    coeffs_y = np.asarray(coeffs_y, dtype=np.float64)
+    ind_spls = np.asarray(ind_spls)
+    t_spls = np.asarray(t_spls, dtype=np.float64)
+    if coeffs_x.shape[0] != coeffs_y.shape[0]:
+        raise ValueError("Coefficient matrices must have the same length!")
+    if ind_spls.size != t_spls.size:
+        raise ValueError("ind_spls and t_spls must have the same length!")
+    if not calc_curv and calc_dcurv:
+        raise ValueError("dkappa cannot be calculated without kappa!")
+    psi, kappa, dkappa = _b.calc_head_curv_batch(_up(coeffs_x), _up(coeffs_y), _up(ind_spls, torch.int32), _up(t_spls),
+                                                 calc_curv=calc_curv, calc_dcurv=calc_dcurv)
+    psi = psi[0].cpu().numpy()
+    kap = kappa[0].cpu().numpy() if calc_curv else 0.0
+    if calc_dcurv:
+        return psi, kap, dkappa[0].cpu().numpy()
+    return psi, kap
+
+
+def iqp_handler(reftrack: np.ndarray, normvectors: np.ndarray, A, kappa_bound: float, w_veh: float,
+                print_debug: bool, plot_debug: bool, stepsize_interp: float, iters_min: int = 3,
+                curv_error_allowed: float = 0.01) -> tuple:
+    """tph.iqp_handler.iqp_handler -> (alpha_mincurv_tmp, reftrack_tmp, normvectors_tmp) of the last
+    iteration.  Unlike tph the caller's reftrack is not modified in place (tph aliases it on iteration 1)."""
+    reftrack = np.asarray(reftrack, dtype=np.float64)
+    normvectors = np.asarray(normvectors, dtype=np.float64)
+    h = h_from_system(A, reftrack.shape[0])
+    res = _b.iqp_batch(_up(reftrack), _up(normvectors), _up(h), kappa_bound, float(w_veh), float(stepsize_interp),
+                       iters_min=int(iters_min), curv_error_allowed=float(curv_error_allowed))
+    _raise_status(int(res["status"][0].item()))
+    n = int(res["n_pts"][0].item())
+    if print_debug:
+        print("Minimum curvature IQP: %i iterations, curv_error_max: %.4frad/m"
+              % (int(res["outer_iters"][0].item()), float(res["curv_error_max"][0].item())))
+    return (res["alpha"][0, :n].cpu().numpy(), res["reftrack"][0, :n].cpu().numpy(), res["normvec"][0, :n].cpu().numpy())

@@ -1,0 +1,165 @@
+/*
+ * mincurv_b200.h -- C-ABI of the B200-native batched minimum-curvature / shortest-path raceline QP path.
+ *
+ * Every entry point replaces one function of the third-party package the reference calls
+ * (trajectory_planning_helpers==0.76, /root/reference/requirements.txt:3); the reference-side
+ * call site that fixes its meaning is cited on each declaration.  The reference has no native
+ * boundary of its own on this path (it is pure Python above quadprog's Cython shim), so this header
+ * is what a ctypes binding inside tph would bind -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers (e.g. torch.Tensor.data_ptr()); nothing is allocated or freed
+ *     by the library: the caller passes a workspace of mc_*_workspace_bytes() bytes;
+ *   - all arrays are float64 unless stated, batch-major, row-major, padded to n_max points per track;
+ *     n_pts[b] (int32, may be NULL => every track has n_max points) is the true size of track b;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous and stream-ordered;
+ *   - return value: 0 = ok, <0 = bad argument (-1), CUDA error (-2), workspace too small (-3);
+ *   - per-instance results are reported in status[b] (int32):
+ *       0 ok | 1 track too narrow ("Problem not solvable, track might be too small ...", tph RuntimeError)
+ *       2 iteration cap reached | 3 numerical breakdown (non-positive pivot)
+ *       4 curvature rows |k_ref + E alpha| <= kappa_bound active/violated at the box-only optimum
+ *         (the result is then the optimum of the box-constrained QP only).
+ */
+#ifndef MINCURV_B200_H
+#define MINCURV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC_OK 0
+#define MC_EINVAL (-1)
+#define MC_ECUDA (-2)
+#define MC_EWORKSPACE (-3)
+
+#define MC_STATUS_OK 0
+#define MC_STATUS_TOO_NARROW 1
+#define MC_STATUS_MAXITER 2
+#define MC_STATUS_BREAKDOWN 3
+#define MC_STATUS_KAPPA_ACTIVE 4
+
+/* library version (major*10000 + minor*100 + patch) and last CUDA error text of this thread */
+int mc_version(void);
+const char *mc_last_error(void);
+
+/* -------------------------------------------------------------------------------------------------
+ * tph.calc_splines.calc_splines(path, el_lengths=None, psi_s=None, psi_e=None, use_dist_scaling=True)
+ * closed-path branch -- call sites /root/reference/helper_funcs_glob/src/prep_track.py:48-51,
+ * /root/reference/main_globaltraj.py:568.
+ *   xy        [B][n_max][xy_stride] : points (x at +0, y at +1); xy_stride = 2 (a path) or 4 (a reftrack)
+ *   el_lengths[B][n_max] or NULL    : segment lengths |p_{i+1}-p_i| override (tph's el_lengths argument)
+ *   use_dist_scaling                : 1 => chord-length scaling between neighbouring segments, 0 => none
+ *   coeffs_x/y[B][n_max][4]         : a0..a3 of every segment, local parameter t in [0,1]
+ *   normvec   [B][n_max][2]         : right-pointing unit normals (t = 0 derivative rotated by -90 deg)
+ *   h_out     [B][n_max]            : the per-segment parameter scale the system matrix M encodes
+ *                                     (scaling_i = h_i / h_{i+1}; all ones without dist scaling) --
+ *                                     replaces the dense 4N x 4N matrix tph returns as `M`
+ * workspace: mc_calc_splines_workspace_bytes(B, n_max)
+ */
+size_t mc_calc_splines_workspace_bytes(int B, int n_max);
+int mc_calc_splines_batch(int B, int n_max, const int32_t *n_pts,
+                          const double *xy, int xy_stride, const double *el_lengths, int use_dist_scaling,
+                          double *coeffs_x, double *coeffs_y, double *normvec, double *h_out,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
+/* -------------------------------------------------------------------------------------------------
+ * tph.opt_min_curv.opt_min_curv(reftrack, normvectors, A, kappa_bound, w_veh, ...)  (closed=True)
+ * -- call sites /root/reference/main_globaltraj.py:264-271 and :344-350; the QP it hands to
+ * quadprog.solve_qp is solved here by a primal-dual interior-point method.
+ *   reftrack  [B][n_max][4]  : x, y, w_tr_right, w_tr_left
+ *   normvec   [B][n_max][2]
+ *   h         [B][n_max]     : parameter scales of the spline system (h_out of mc_calc_splines_batch;
+ *                              what the reference passes as the dense matrix `A`)
+ *   w_veh_batch [B] or NULL  : per-instance vehicle width; NULL => the scalar w_veh for all
+ *   alpha     [B][n_max]     : lateral shift of every point along its normal [m]
+ *   curv_error_max [B]       : tph's linearisation error (second tuple element of opt_min_curv)
+ *   kappa_lin_max  [B] or NULL : max |k_ref + E alpha| of the linearised curvature at the solution
+ *   iters     [B] or NULL    : interior-point iterations used (int32)
+ */
+size_t mc_mincurv_workspace_bytes(int B, int n_max);
+int mc_mincurv_solve_batch(int B, int n_max, const int32_t *n_pts,
+                           const double *reftrack, const double *normvec, const double *h,
+                           double kappa_bound, double w_veh, const double *w_veh_batch,
+                           double *alpha, double *curv_error_max, double *kappa_lin_max,
+                           int32_t *status, int32_t *iters,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
+/* The three stages of mc_mincurv_solve_batch as separate stream-ordered calls on the same workspace
+ * (assembly of the banded QP, interior-point solve, post-solve curvature check / linearisation error);
+ * mc_mincurv_solve_batch is exactly setup -> pdip -> finalize.  Exposed so that a caller can time or
+ * overlap the stages; arguments as above. */
+int mc_mincurv_setup_batch(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
+                           const double *h, double w_veh, const double *w_veh_batch, int32_t *status,
+                           void *workspace, size_t workspace_bytes, void *stream);
+int mc_mincurv_pdip_batch(int B, int n_max, const int32_t *n_pts, double *alpha, int32_t *status, int32_t *iters,
+                          void *workspace, size_t workspace_bytes, void *stream);
+int mc_mincurv_finalize_batch(int B, int n_max, const int32_t *n_pts, const double *alpha, double kappa_bound,
+                              double *curv_error_max, double *kappa_lin_max, int32_t *status,
+                              void *workspace, size_t workspace_bytes, void *stream);
+
+/* -------------------------------------------------------------------------------------------------
+ * tph.opt_shortest_path.opt_shortest_path(reftrack, normvectors, w_veh, print_debug)
+ * -- call site /root/reference/main_globaltraj.py:286-290.
+ */
+size_t mc_shortest_path_workspace_bytes(int B, int n_max);
+int mc_shortest_path_solve_batch(int B, int n_max, const int32_t *n_pts,
+                                 const double *reftrack, const double *normvec,
+                                 double w_veh, const double *w_veh_batch,
+                                 double *alpha, int32_t *status, int32_t *iters,
+                                 void *workspace, size_t workspace_bytes, void *stream);
+
+/* -------------------------------------------------------------------------------------------------
+ * tph.create_raceline.create_raceline(refline, normvectors, alpha, stepsize_interp)
+ * -- call site /root/reference/main_globaltraj.py:371-376 (9-tuple; the dense A_raceline is replaced
+ * by nothing: without distance scaling every parameter scale is 1) fused with
+ * tph.calc_head_curv_an.calc_head_curv_an(coeffs_x, coeffs_y, ind_spls, t_spls)
+ * -- call site /root/reference/main_globaltraj.py:383-387.
+ *   refline [B][n_max][ref_stride] (x at +0, y at +1), normvec [B][n_max][2], alpha [B][n_max]
+ *   outputs per track: coeffs_x/y [B][n_max][4], spline_lengths [B][n_max],
+ *   n_out [B] (int32) and, padded to n_out_max: raceline_interp [.][2], spline_inds (int32), t_values,
+ *   s_interp, el_lengths_interp, psi, kappa (psi/kappa may be NULL).
+ *   A track whose n_out would exceed n_out_max gets n_out = -(required size) and no resampled output.
+ */
+size_t mc_create_raceline_workspace_bytes(int B, int n_max);
+int mc_create_raceline_batch(int B, int n_max, const int32_t *n_pts,
+                             const double *refline, int ref_stride, const double *normvec, const double *alpha,
+                             double stepsize_interp, int n_out_max,
+                             double *coeffs_x, double *coeffs_y, double *spline_lengths,
+                             int32_t *n_out, double *raceline_interp, int32_t *spline_inds, double *t_values,
+                             double *s_interp, double *el_lengths_interp, double *psi, double *kappa,
+                             void *workspace, size_t workspace_bytes, void *stream);
+
+/* tph.calc_head_curv_an.calc_head_curv_an stand-alone (any (spline index, t) pairs), call site
+ * /root/reference/main_globaltraj.py:383-387.  dkappa may be NULL (calc_dcurv=False). */
+int mc_calc_head_curv_batch(int B, int n_max, const double *coeffs_x, const double *coeffs_y,
+                            int n_eval_max, const int32_t *n_eval, const int32_t *ind_spls, const double *t_spls,
+                            double *psi, double *kappa, double *dkappa, void *stream);
+
+/* -------------------------------------------------------------------------------------------------
+ * One re-linearisation step of tph.iqp_handler.iqp_handler (call site
+ * /root/reference/main_globaltraj.py:273-284): given alpha on the current reftrack,
+ * build the next reftrack on the re-sampled raceline (create_raceline with stepsize_interp, widths
+ * shifted by alpha and interpolated linearly in t) and its splines without distance scaling.
+ *   in : reftrack [B][n_max][4], normvec [B][n_max][2], alpha [B][n_max], n_pts [B]
+ *   out: reftrack_new [B][n_max_new][4], normvec_new [B][n_max_new][2], n_pts_new [B]
+ *        (n_pts_new[b] = -(required) if it would exceed n_max_new)
+ *   active [B] (int32) or NULL: tracks with active[b] == 0 are copied through unchanged.
+ */
+size_t mc_iqp_relinearise_workspace_bytes(int B, int n_max, int n_max_new);
+int mc_iqp_relinearise_batch(int B, int n_max, const int32_t *n_pts, const int32_t *active,
+                             const double *reftrack, const double *normvec, const double *alpha,
+                             double stepsize_interp, int n_max_new,
+                             double *reftrack_new, double *normvec_new, int32_t *n_pts_new,
+                             void *workspace, size_t workspace_bytes, void *stream);
+
+/* alpha[b][:] *= scale_batch[b] (or the scalar `scale` when scale_batch is NULL): the damping
+ * `alpha *= iter / iters_min` of tph.iqp_handler. */
+int mc_scale_alpha_batch(int B, int n_max, double *alpha, const double *scale_batch, double scale, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINCURV_B200_H */

@@ -1,0 +1,111 @@
+"""CPU tests (-m "not gpu") of the host side: the C-ABI library loads and exports every symbol declared in
+include/*.h, argument validation happens before any CUDA work, the SplineSystem stand-in reproduces the
+dense matrix of tph.calc_splines, and the package mirrors the tph call surface."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+import global_racetrajectory_optimization_b200 as tph
+from global_racetrajectory_optimization_b200 import _lib, spline_system, synth
+from oracle import tph_dense as T
+
+
+def _declared_symbols():
+    names = set()
+    inc = os.path.join(ROOT, "include")
+    for fn in os.listdir(inc):
+        if fn.endswith(".h"):
+            txt = open(os.path.join(inc, fn)).read()
+            txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+            names |= set(re.findall(r"\b(mc_[a-z0-9_]+)\s*\(", txt))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert declared, "no declarations parsed from include/*.h"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+    assert lib.mc_version() >= 100
+
+
+def test_workspace_queries_and_argument_validation_without_gpu():
+    lib = _lib.load()
+    assert lib.mc_mincurv_workspace_bytes(4, 1000) > 4 * 1000 * 34 * 8
+    assert lib.mc_mincurv_workspace_bytes(4, 10) == 0            # below the supported minimum
+    assert lib.mc_calc_splines_workspace_bytes(2, 500) % 256 == 0
+    assert lib.mc_mincurv_workspace_bytes(8, 1000) == 2 * lib.mc_mincurv_workspace_bytes(4, 1000)
+    # NULL / bad arguments are rejected before any CUDA call
+    assert lib.mc_calc_splines_batch(1, 100, None, None, 2, None, 1, None, None, None, None, None, 0, None) == -1
+    assert b"bad argument" in lib.mc_last_error()
+    assert lib.mc_mincurv_solve_batch(1, 100, None, None, None, None, 0.12, 2.0, None, None, None, None, None, None,
+                                      None, 0, None) == -1
+    dummy = ctypes.c_void_p(4096)
+    assert lib.mc_mincurv_solve_batch(1, 10, None, dummy, dummy, dummy, 0.12, 2.0, None, dummy, dummy, None, dummy, None,
+                                      None, 0, None) == -1        # n_max too small
+    assert lib.mc_mincurv_solve_batch(1, 100, None, dummy, dummy, dummy, 0.12, 2.0, None, dummy, dummy, None, dummy, None,
+                                      None, 0, None) == -3        # workspace too small
+    assert lib.mc_create_raceline_batch(1, 100, None, dummy, 3, dummy, dummy, 2.0, 10, dummy, dummy, dummy, dummy, dummy,
+                                        dummy, dummy, dummy, dummy, None, None, dummy, 1 << 30, None) == -1   # stride 3
+
+
+def test_spline_system_materialises_the_tph_matrix():
+    rt = synth.make_track(4, 90)
+    path = np.vstack((rt[:, :2], rt[0, :2]))
+    _, _, A, _ = T.calc_splines(path)
+    el = np.sqrt(np.sum(np.diff(path, axis=0) ** 2, axis=1))
+    S = spline_system.SplineSystem(el)
+    assert S.shape == A.shape
+    assert np.abs(np.asarray(S) - A).max() < 1e-12
+    h = spline_system.h_from_system(A, 90)          # dense matrix -> scales (only ratios matter)
+    assert np.allclose(h / h[0], el / el[0], rtol=1e-12)
+    assert spline_system.h_from_system(S, 90) is S.h
+    with pytest.raises(RuntimeError, match="wrong dimensions"):
+        spline_system.h_from_system(A, 91)
+    _, _, A1, _ = T.calc_splines(path, use_dist_scaling=False)
+    assert np.abs(np.asarray(spline_system.SplineSystem(np.ones(90))) - A1).max() == 0.0
+
+
+def test_call_surface_matches_the_reference_call_sites():
+    """Keyword names used by /root/reference/main_globaltraj.py:264-290,371-387 and prep_track.py:50."""
+    sig = lambda f: list(inspect.signature(f).parameters)
+    assert sig(tph.calc_splines.calc_splines) == ["path", "el_lengths", "psi_s", "psi_e", "use_dist_scaling"]
+    assert sig(tph.opt_min_curv.opt_min_curv)[:7] == ["reftrack", "normvectors", "A", "kappa_bound", "w_veh",
+                                                       "print_debug", "plot_debug"]
+    assert sig(tph.iqp_handler.iqp_handler) == ["reftrack", "normvectors", "A", "kappa_bound", "w_veh", "print_debug",
+                                                "plot_debug", "stepsize_interp", "iters_min", "curv_error_allowed"]
+    assert sig(tph.opt_shortest_path.opt_shortest_path) == ["reftrack", "normvectors", "w_veh", "print_debug"]
+    assert sig(tph.create_raceline.create_raceline) == ["refline", "normvectors", "alpha", "stepsize_interp"]
+    assert sig(tph.calc_head_curv_an.calc_head_curv_an) == ["coeffs_x", "coeffs_y", "ind_spls", "t_spls", "calc_curv",
+                                                            "calc_dcurv"]
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    rt = synth.make_track(1, 100)
+    path = np.vstack((rt[:, :2], rt[0, :2]))
+    with pytest.raises(_lib.MinCurvLibError, match="no CPU fallback"):
+        tph.calc_splines.calc_splines(path=path)
+    with pytest.raises(RuntimeError, match="Headings must be provided"):
+        tph.calc_splines.calc_splines(path=path[:-1])
+
+
+def test_synthetic_tracks_are_deterministic_and_well_posed():
+    a, b = synth.make_track(7, 300), synth.make_track(7, 300)
+    assert np.array_equal(a, b) and not np.array_equal(a, synth.make_track(8, 300))
+    k = synth.discrete_curvature(a[:, :2])
+    assert 0.02 < np.abs(k).max() < 0.25
+    assert (np.maximum(a[:, 2], a[:, 3]) * np.abs(k)).max() <= 0.7 + 1e-9
+    d = np.linalg.norm(np.diff(np.vstack((a[:, :2], a[0, :2])), axis=0), axis=1)
+    assert d.std() / d.mean() < 0.02                  # equidistant points
+    j = synth.jitter_widths(a, 3)
+    assert np.array_equal(j[:, :2], a[:, :2]) and np.abs(j[:, 2:] / a[:, 2:] - 1).max() <= 0.1 + 1e-12
