@@ -108,7 +108,7 @@ int mc_mincurv_pdip_batch(int B, int n_max, const int32_t *n_pts, double *alpha,
     mc::PdipParams prm;
     prm.max_iter = 40;
     prm.mu_rel = 1e-11;
-    prm.rd_rel = 1e-9;
+    prm.rd_rel = 1e-8;
     prm.eta = 0.995;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

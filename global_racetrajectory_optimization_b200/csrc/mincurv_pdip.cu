@@ -415,7 +415,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
         const double *LB = vec(slab, L, V_LB), *UB = vec(slab, L, V_UB), *F = vec(slab, L, V_F);
         double *AL = vec(slab, L, V_ALPHA), *LU = vec(slab, L, V_LU), *LL = vec(slab, L, V_LL), *RD = vec(slab, L, V_RD);
         double *RHS = vec(slab, L, V_RHS), *DX = vec(slab, L, V_DX), *DD = vec(slab, L, V_DD);
-        double *TU = vec(slab, L, V_DLU), *TL = vec(slab, L, V_DLL);
+        double *TU = vec(slab, L, V_DLU), *TL = vec(slab, L, V_DLL), *SU = vec(slab, L, V_SU), *SL = vec(slab, L, V_SL);
         double *YP = vec(slab, L, V_T4), *ZP = vec(slab, L, V_T5), *G0 = vec(slab, L, V_T0);
         const int nb = (n - 32 + 31) / 32;
         if (threadIdx.x == 0) sh.flag = 0;
@@ -442,7 +442,11 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             LU[i] = lu; LL[i] = ll;
             RD[i] = gi + lu - ll;
             const double a = AL[i];
-            musum += (UB[i] - a) * lu + (a - LB[i]) * ll;
+            // slacks are carried as variables of their own: recomputing ub - alpha loses them to
+            // cancellation once s << eps |alpha| (late iterations), see DESIGN.md
+            const double su = UB[i] - a, sl = a - LB[i];
+            SU[i] = su; SL[i] = sl;
+            musum += su * lu + sl * ll;
         }
         musum = block_reduce<0>(musum, sh.red);
         const double mu0 = musum / (2.0 * n);
@@ -454,7 +458,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
         for (it = 0; it < prm.max_iter; ++it) {
             // ---- barrier diagonal and affine right-hand side ----
             for (int i = threadIdx.x; i < n; i += PD_THREADS) {
-                const double a = AL[i], su = UB[i] - a, sl = a - LB[i], lu = LU[i], ll = LL[i];
+                const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i];
                 DD[i] = lu / su + ll / sl;
                 RHS[i] = -RD[i] + lu - ll;
             }
@@ -464,7 +468,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             // ---- affine step lengths, centring parameter ----
             double ap = 1.0, ad = 1.0;
             for (int i = threadIdx.x; i < n; i += PD_THREADS) {
-                const double a = AL[i], su = UB[i] - a, sl = a - LB[i], lu = LU[i], ll = LL[i], dx = DX[i];
+                const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i];
                 const double dlu = -lu + lu * dx / su, dll = -ll - ll * dx / sl;
                 if (dx > 0.0) ap = fmin(ap, su / dx);
                 if (dx < 0.0) ap = fmin(ap, -sl / dx);
@@ -475,7 +479,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             ad = block_reduce<2>(ad, sh.red);
             double mua = 0.0;
             for (int i = threadIdx.x; i < n; i += PD_THREADS) {
-                const double a = AL[i], su = UB[i] - a, sl = a - LB[i], lu = LU[i], ll = LL[i], dx = DX[i];
+                const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i];
                 const double dlu = -lu + lu * dx / su, dll = -ll - ll * dx / sl;
                 mua += (su - ap * dx) * (lu + ad * dlu) + (sl + ap * dx) * (ll + ad * dll);
             }
@@ -485,7 +489,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             const double smu = sigma * mu;
             // ---- corrector right-hand side ----
             for (int i = threadIdx.x; i < n; i += PD_THREADS) {
-                const double a = AL[i], su = UB[i] - a, sl = a - LB[i], lu = LU[i], ll = LL[i], dx = DX[i];
+                const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i];
                 const double dlu = -lu + lu * dx / su, dll = -ll - ll * dx / sl;
                 const double tu = smu - su * lu - (-dx) * dlu;
                 const double tl = smu - sl * ll - dx * dll;
@@ -496,7 +500,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             solve(sh, tiles, RHS, DX, YP, ZP, n, nb);
             ap = 1e300; ad = 1e300;
             for (int i = threadIdx.x; i < n; i += PD_THREADS) {
-                const double a = AL[i], su = UB[i] - a, sl = a - LB[i], lu = LU[i], ll = LL[i], dx = DX[i];
+                const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i];
                 const double dlu = (TU[i] + lu * dx) / su, dll = (TL[i] - ll * dx) / sl;
                 if (dx > 0.0) ap = fmin(ap, su / dx);
                 if (dx < 0.0) ap = fmin(ap, -sl / dx);
@@ -507,18 +511,20 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             ad = fmin(1.0, prm.eta * block_reduce<2>(ad, sh.red));
             double musum2 = 0.0, rdmax = 0.0;
             for (int i = threadIdx.x; i < n; i += PD_THREADS) {
-                const double a = AL[i], su = UB[i] - a, sl = a - LB[i], lu = LU[i], ll = LL[i], dx = DX[i];
+                const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i];
                 const double dlu = (TU[i] + lu * dx) / su, dll = (TL[i] - ll * dx) / sl;
-                const double an = a + ap * dx, lun = lu + ad * dlu, lln = ll + ad * dll;
+                const double an = AL[i] + ap * dx, lun = lu + ad * dlu, lln = ll + ad * dll;
+                const double sun = su - ap * dx, sln = sl + ap * dx;
                 // H dx = rhs - D dx  (M dx = rhs)
                 const double rdn = RD[i] + ap * (RHS[i] - DD[i] * dx) + ad * (dlu - dll);
-                AL[i] = an; LU[i] = lun; LL[i] = lln; RD[i] = rdn;
-                musum2 += (UB[i] - an) * lun + (an - LB[i]) * lln;
+                AL[i] = an; LU[i] = lun; LL[i] = lln; RD[i] = rdn; SU[i] = sun; SL[i] = sln;
+                musum2 += sun * lun + sln * lln;
                 rdmax = fmax(rdmax, fabs(rdn));
             }
             mu = block_reduce<0>(musum2, sh.red) / (2.0 * n);
             rdmax = block_reduce<1>(rdmax, sh.red);
             if (mu <= prm.mu_rel * mu0 && rdmax <= rd_tol) { result = 0; ++it; break; }
+            if (mu <= 1e-4 * prm.mu_rel * mu0) { result = (rdmax <= 1e3 * rd_tol) ? 0 : 2; ++it; break; }   // complementarity exhausted
         }
         __syncthreads();
         for (int i = threadIdx.x; i < n_max; i += PD_THREADS) aout[i] = (i < n) ? AL[i] : 0.0;

@@ -15,7 +15,7 @@ enum Vec : int {
     V_PX, V_PY, V_NX, V_NY, V_MX, V_MY, V_XP, V_YP, V_SX, V_SY, V_KREF,
     V_LB, V_UB, V_F,
     V_T0, V_T1, V_T2, V_T3, V_T4, V_T5,
-    V_ALPHA, V_LU, V_LL, V_RD, V_RHS, V_DX, V_DD, V_DLU, V_DLL,
+    V_ALPHA, V_LU, V_LL, V_RD, V_RHS, V_DX, V_DD, V_DLU, V_DLL, V_SU, V_SL,
     NUM_VEC
 };
 

@@ -12,7 +12,7 @@
 
 namespace mc {
 
-enum SpVec : int { SP_LB = 0, SP_UB, SP_F, SP_OFF, SP_DG, SP_AL, SP_LU, SP_LL, SP_RD, SP_X, SP_CP, SP_MI, SP_Q, SP_TU, SP_TL, SP_DD, SP_RHS, SP_NUM };
+enum SpVec : int { SP_LB = 0, SP_UB, SP_F, SP_OFF, SP_DG, SP_AL, SP_LU, SP_LL, SP_RD, SP_X, SP_CP, SP_MI, SP_Q, SP_TU, SP_TL, SP_DD, SP_RHS, SP_SU, SP_SL, SP_NUM };
 
 size_t shortest_path_ws_doubles(int n_max) { return (size_t)SP_NUM * n_max; }
 
@@ -114,22 +114,24 @@ shortest_path_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, const 
         const double lu = fmax(-g, 0.0) + lam0, ll = fmax(g, 0.0) + lam0;
         w(SP_LU, i) = lu; w(SP_LL, i) = ll; w(SP_RD, i) = g + lu - ll;
         const double a = w(SP_AL, i);
-        musum += (w(SP_UB, i) - a) * lu + (a - w(SP_LB, i)) * ll;
+        const double su = w(SP_UB, i) - a, sl = a - w(SP_LB, i);
+        w(SP_SU, i) = su; w(SP_SL, i) = sl;
+        musum += su * lu + sl * ll;
     }
     const double mu0 = musum / (2.0 * n);
-    const double rd_tol = 1e-9 * (fmaxv + gmax) + 1e-300;
+    const double rd_tol = 1e-8 * (fmaxv + gmax) + 1e-300;
     double mu = mu0;
     int it = 0, result = MC_STATUS_MAXITER;
     for (it = 0; it < 50; ++it) {
         for (int i = 0; i < n; ++i) {
-            const double a = w(SP_AL, i), su = w(SP_UB, i) - a, sl = a - w(SP_LB, i), lu = w(SP_LU, i), ll = w(SP_LL, i);
+            const double su = w(SP_SU, i), sl = w(SP_SL, i), lu = w(SP_LU, i), ll = w(SP_LL, i);
             w(SP_DD, i) = lu / su + ll / sl;
             w(SP_RHS, i) = -w(SP_RD, i) + lu - ll;
         }
         cyc_solve(w, n, true);
         double ap = 1.0, ad = 1.0;
         for (int i = 0; i < n; ++i) {
-            const double a = w(SP_AL, i), su = w(SP_UB, i) - a, sl = a - w(SP_LB, i), lu = w(SP_LU, i), ll = w(SP_LL, i);
+            const double su = w(SP_SU, i), sl = w(SP_SL, i), lu = w(SP_LU, i), ll = w(SP_LL, i);
             const double dx = w(SP_X, i);
             const double dlu = -lu + lu * dx / su, dll = -ll - ll * dx / sl;
             if (dx > 0.0) ap = fmin(ap, su / dx);
@@ -139,7 +141,7 @@ shortest_path_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, const 
         }
         double mua = 0.0;
         for (int i = 0; i < n; ++i) {
-            const double a = w(SP_AL, i), su = w(SP_UB, i) - a, sl = a - w(SP_LB, i), lu = w(SP_LU, i), ll = w(SP_LL, i);
+            const double su = w(SP_SU, i), sl = w(SP_SL, i), lu = w(SP_LU, i), ll = w(SP_LL, i);
             const double dx = w(SP_X, i);
             const double dlu = -lu + lu * dx / su, dll = -ll - ll * dx / sl;
             mua += (su - ap * dx) * (lu + ad * dlu) + (sl + ap * dx) * (ll + ad * dll);
@@ -149,7 +151,7 @@ shortest_path_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, const 
         sigma = sigma * sigma * sigma;
         const double smu = sigma * mu;
         for (int i = 0; i < n; ++i) {
-            const double a = w(SP_AL, i), su = w(SP_UB, i) - a, sl = a - w(SP_LB, i), lu = w(SP_LU, i), ll = w(SP_LL, i);
+            const double su = w(SP_SU, i), sl = w(SP_SL, i), lu = w(SP_LU, i), ll = w(SP_LL, i);
             const double dx = w(SP_X, i);
             const double dlu = -lu + lu * dx / su, dll = -ll - ll * dx / sl;
             const double tu = smu - su * lu + dx * dlu, tl = smu - sl * ll - dx * dll;
@@ -159,7 +161,7 @@ shortest_path_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, const 
         cyc_solve(w, n, false);
         ap = 1e300; ad = 1e300;
         for (int i = 0; i < n; ++i) {
-            const double a = w(SP_AL, i), su = w(SP_UB, i) - a, sl = a - w(SP_LB, i), lu = w(SP_LU, i), ll = w(SP_LL, i);
+            const double su = w(SP_SU, i), sl = w(SP_SL, i), lu = w(SP_LU, i), ll = w(SP_LL, i);
             const double dx = w(SP_X, i);
             const double dlu = (w(SP_TU, i) + lu * dx) / su, dll = (w(SP_TL, i) - ll * dx) / sl;
             if (dx > 0.0) ap = fmin(ap, su / dx);
@@ -171,17 +173,19 @@ shortest_path_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, const 
         ad = fmin(1.0, 0.995 * ad);
         double musum2 = 0.0, rdmax = 0.0;
         for (int i = 0; i < n; ++i) {
-            const double a = w(SP_AL, i), su = w(SP_UB, i) - a, sl = a - w(SP_LB, i), lu = w(SP_LU, i), ll = w(SP_LL, i);
+            const double su = w(SP_SU, i), sl = w(SP_SL, i), lu = w(SP_LU, i), ll = w(SP_LL, i);
             const double dx = w(SP_X, i);
             const double dlu = (w(SP_TU, i) + lu * dx) / su, dll = (w(SP_TL, i) - ll * dx) / sl;
-            const double an = a + ap * dx, lun = lu + ad * dlu, lln = ll + ad * dll;
+            const double an = w(SP_AL, i) + ap * dx, lun = lu + ad * dlu, lln = ll + ad * dll;
+            const double sun = su - ap * dx, sln = sl + ap * dx;
             const double rdn = w(SP_RD, i) + ap * (w(SP_RHS, i) - w(SP_DD, i) * dx) + ad * (dlu - dll);
-            w(SP_AL, i) = an; w(SP_LU, i) = lun; w(SP_LL, i) = lln; w(SP_RD, i) = rdn;
-            musum2 += (w(SP_UB, i) - an) * lun + (an - w(SP_LB, i)) * lln;
+            w(SP_AL, i) = an; w(SP_LU, i) = lun; w(SP_LL, i) = lln; w(SP_RD, i) = rdn; w(SP_SU, i) = sun; w(SP_SL, i) = sln;
+            musum2 += sun * lun + sln * lln;
             rdmax = fmax(rdmax, fabs(rdn));
         }
         mu = musum2 / (2.0 * n);
         if (mu <= 1e-11 * mu0 && rdmax <= rd_tol) { result = MC_STATUS_OK; ++it; break; }
+        if (mu <= 1e-15 * mu0) { result = (rdmax <= 1e3 * rd_tol) ? MC_STATUS_OK : MC_STATUS_MAXITER; ++it; break; }
         if (!(mu == mu)) { result = MC_STATUS_BREAKDOWN; break; }
     }
     for (int i = 0; i < n_max; ++i) aout[i] = (i < n) ? w(SP_AL, i) : 0.0;

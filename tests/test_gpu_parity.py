@@ -1,0 +1,246 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI (ctypes) by the tph-style surface and by the
+batched API, against (1) the committed golden vectors of the CPU oracle, (2) the oracle run on the same seeded
+inputs, (3) size-independent properties at BASELINE sizes, and the reference's edge cases.
+
+Tolerances (BASELINE.json north_star): alpha <= 1e-4, kappa <= 1e-3, both as max|diff| / max|ref|."""
+import numpy as np
+import pytest
+
+from conftest import rel_max
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import global_racetrajectory_optimization_b200 as tph  # noqa: E402
+from global_racetrajectory_optimization_b200 import batch as B_, synth  # noqa: E402
+from oracle import tph_dense as T  # noqa: E402
+
+ALPHA_TOL = 1e-4
+KAPPA_TOL = 1e-3
+ALL = ["berlin", "handling", "modena", "synth128", "synth200", "synth333", "synth500", "synth500_narrow", "synth1000"]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _closed(rt):
+    return np.vstack((rt[:, :2], rt[0, :2]))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_calc_splines_matches_golden(golden, name):
+    g = golden(name)
+    cx, cy, M, nv = tph.calc_splines.calc_splines(path=_closed(g["reftrack"]))
+    assert np.abs(cx - g["coeffs_x"]).max() < 1e-9 and np.abs(cy - g["coeffs_y"]).max() < 1e-9
+    assert np.abs(nv - g["normvec"]).max() < 1e-11
+    assert np.allclose(M.scaling, g["scaling"], rtol=1e-12)
+    # without distance scaling (what create_raceline / iqp_handler use)
+    cx1, cy1, M1, nv1 = tph.calc_splines.calc_splines(path=_closed(g["reftrack"]), use_dist_scaling=False)
+    ox, oy, _, onv = T.calc_splines(_closed(g["reftrack"]), use_dist_scaling=False) if g["reftrack"].shape[0] <= 350 else (None,) * 4
+    if ox is not None:
+        assert np.abs(cx1 - ox).max() < 1e-9 and np.abs(nv1 - onv).max() < 1e-11
+    assert np.all(M1.h == 1.0)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_opt_min_curv_matches_golden(golden, name):
+    g = golden(name)
+    rt = g["reftrack"]
+    _, _, M, nv = tph.calc_splines.calc_splines(path=_closed(rt))
+    alpha, cerr = tph.opt_min_curv.opt_min_curv(reftrack=rt, normvectors=nv, A=M, kappa_bound=float(g["kappa_bound"]),
+                                                w_veh=float(g["w_veh"]))
+    assert rel_max(alpha, g["alpha_mincurv"]) <= ALPHA_TOL
+    assert abs(cerr - float(g["curv_error_max"])) <= 1e-3 * float(g["curv_error_max"]) + 1e-7
+    # the dense matrix the reference passes as A works too (scalings are read out of it)
+    if rt.shape[0] <= 210:
+        alpha2, _ = tph.opt_min_curv.opt_min_curv(rt, nv, np.asarray(M), float(g["kappa_bound"]), float(g["w_veh"]))
+        assert rel_max(alpha2, alpha) < 1e-9
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_opt_shortest_path_matches_golden(golden, name):
+    g = golden(name)
+    a = tph.opt_shortest_path.opt_shortest_path(reftrack=g["reftrack"], normvectors=g["normvec"], w_veh=float(g["w_veh"]))
+    assert rel_max(a, g["alpha_shpath"]) <= ALPHA_TOL
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_create_raceline_and_head_curv_match_golden(golden, name):
+    g = golden(name)
+    rl = tph.create_raceline.create_raceline(refline=g["reftrack"][:, :2], normvectors=g["normvec"],
+                                             alpha=g["alpha_mincurv"], stepsize_interp=2.0)
+    assert len(rl) == 9 and rl[0].shape == g["rl_raceline_interp"].shape
+    assert np.abs(rl[0] - g["rl_raceline_interp"]).max() < 1e-8
+    assert np.array_equal(rl[4], g["rl_spline_inds"])
+    assert np.abs(rl[5] - g["rl_t_values"]).max() < 1e-9 and np.abs(rl[6] - g["rl_s"]).max() < 1e-8
+    assert np.abs(rl[7] - g["rl_spline_lengths"]).max() < 1e-10 and np.abs(rl[8] - g["rl_el_lengths"]).max() < 1e-8
+    psi, kappa = tph.calc_head_curv_an.calc_head_curv_an(coeffs_x=rl[2], coeffs_y=rl[3], ind_spls=rl[4], t_spls=rl[5])
+    assert rel_max(kappa, g["rl_kappa"]) <= KAPPA_TOL
+    dpsi = np.abs(psi - g["rl_psi"])
+    assert np.minimum(dpsi, 2 * np.pi - dpsi).max() < 1e-9
+    psi3, kappa3, dk = tph.calc_head_curv_an.calc_head_curv_an(rl[2], rl[3], rl[4], rl[5], calc_curv=True, calc_dcurv=True)
+    _, _, dk_o = T.calc_head_curv_an(g["rl_coeffs_x"], g["rl_coeffs_y"], g["rl_spline_inds"], g["rl_t_values"], True, True)
+    assert rel_max(dk, dk_o) < 1e-6
+
+
+def test_full_chain_alpha_kappa_raceline_vs_oracle_on_seeded_inputs():
+    """alpha -> raceline -> kappa, everything from the GPU, against everything from the oracle."""
+    for seed, n in [(31, 150), (32, 260)]:
+        rt = synth.make_track(seed, n)
+        cx, cy, M, nv = tph.calc_splines.calc_splines(path=_closed(rt))
+        alpha, _ = tph.opt_min_curv.opt_min_curv(rt, nv, M, 0.12, 2.0)
+        rl = tph.create_raceline.create_raceline(rt[:, :2], nv, alpha, 2.0)
+        psi, kappa = tph.calc_head_curv_an.calc_head_curv_an(rl[2], rl[3], rl[4], rl[5])
+        ocx, ocy, oA, onv = T.calc_splines(_closed(rt))
+        oalpha, _ = T.opt_min_curv(rt, onv, oA, 0.12, 2.0)
+        orl = T.create_raceline(rt[:, :2], onv, oalpha, 2.0)
+        opsi, okappa = T.calc_head_curv_an(orl[2], orl[3], orl[4], orl[5])
+        assert rel_max(alpha, oalpha) <= ALPHA_TOL
+        assert rl[0].shape == orl[0].shape and rel_max(rl[0], orl[0]) <= 1e-6
+        assert rel_max(kappa, okappa) <= KAPPA_TOL
+
+
+@pytest.mark.parametrize("name", ["synth128", "synth333", "handling", "berlin"])
+def test_iqp_handler_matches_golden(golden, name):
+    g = golden(name)
+    rt = g["reftrack"].copy()
+    _, _, M, nv = tph.calc_splines.calc_splines(path=_closed(rt))
+    a, rt_new, nv_new = tph.iqp_handler.iqp_handler(reftrack=rt, normvectors=nv, A=M, kappa_bound=float(g["kappa_bound"]),
+                                                    w_veh=float(g["w_veh"]), print_debug=False, plot_debug=False,
+                                                    stepsize_interp=3.0, iters_min=3, curv_error_allowed=0.01)
+    assert np.array_equal(rt, g["reftrack"])                    # caller's array untouched (documented deviation)
+    assert rt_new.shape == g["iqp_reftrack"].shape and nv_new.shape == g["iqp_normvec"].shape
+    assert rel_max(a, g["iqp_alpha"]) <= 10 * ALPHA_TOL            # three chained QPs + resampling
+    assert np.abs(rt_new - g["iqp_reftrack"]).max() <= 1e-3
+    assert np.abs(nv_new - g["iqp_normvec"]).max() <= 1e-4
+
+
+def test_batch_api_ragged_sizes_statuses_and_determinism(golden):
+    dev = torch.device("cuda")
+    names = ["synth128", "synth333", "synth200", "handling"]
+    gs = [golden(n) for n in names]
+    n_max = max(g["reftrack"].shape[0] for g in gs)
+    B = len(gs) + 2
+    rt = np.zeros((B, n_max, 4))
+    npts = np.zeros(B, dtype=np.int32)
+    for i, g in enumerate(gs):
+        n = g["reftrack"].shape[0]
+        rt[i, :n] = g["reftrack"]
+        npts[i] = n
+    rt[4, :gs[0]["reftrack"].shape[0]] = gs[0]["reftrack"]       # duplicate of instance 0
+    npts[4] = npts[0]
+    rt[5, :200] = gs[2]["reftrack"]
+    rt[5, :200, 2:] = 0.4                                         # narrower than the vehicle: tph raises RuntimeError
+    npts[5] = 200
+    rtd, nd = torch.tensor(rt, device=dev), torch.tensor(npts, device=dev)
+    cx, cy, nv, h = B_.calc_splines_batch(rtd, n_pts=nd)
+    res = B_.opt_min_curv_batch(rtd, nv, h, 0.12, 2.0, n_pts=nd)
+    st = res["status"].cpu().numpy()
+    assert list(st[:5]) == [0, 0, 0, 0, 0] and st[5] == 1
+    al = res["alpha"].cpu().numpy()
+    for i, g in enumerate(gs):
+        n = npts[i]
+        assert rel_max(al[i, :n], g["alpha_mincurv"]) <= ALPHA_TOL
+        assert np.all(al[i, n:] == 0.0)
+    assert np.array_equal(al[0], al[4])                            # identical instances -> bit-identical results
+    assert np.all(al[5] == 0.0)
+    with pytest.raises(RuntimeError, match="Problem not solvable"):
+        tph.opt_min_curv.opt_min_curv(rt[5, :200], nv[5, :200].cpu().numpy(), tph.SplineSystem(h[5, :200].cpu().numpy()), 0.12, 2.0)
+    sp = B_.opt_shortest_path_batch(rtd, nv, 2.0, n_pts=nd)
+    asp = sp["alpha"].cpu().numpy()
+    for i, g in enumerate(gs):
+        assert rel_max(asp[i, :npts[i]], g["alpha_shpath"]) <= ALPHA_TOL
+    # per-instance vehicle width == scalar vehicle width
+    res2 = B_.opt_min_curv_batch(rtd, nv, h, 0.12, torch.full((B,), 2.0, device=dev, dtype=torch.float64), n_pts=nd)
+    assert torch.equal(res2["alpha"], res["alpha"])
+
+
+def test_small_tracks_are_rejected_loudly():
+    rt = synth.make_track(1, 60)
+    _, _, M, nv = tph.calc_splines.calc_splines(path=_closed(rt))
+    with pytest.raises(NotImplementedError):
+        tph.opt_min_curv.opt_min_curv(rt, nv, M, 0.12, 2.0)
+    with pytest.raises(RuntimeError, match="Array size"):
+        tph.opt_min_curv.opt_min_curv(synth.make_track(1, 100), nv, M, 0.12, 2.0)
+
+
+def test_properties_at_baseline_size():
+    """N = 1000 batch: size-independent properties instead of the (slow) oracle.
+    KKT conditions of every returned alpha w.r.t. the banded H the kernel assembled (read back from its
+    workspace), translation/rotation invariance, and reversal symmetry."""
+    dev = torch.device("cuda")
+    n, B = 1000, 24
+    base = synth.make_batch(500, 6, n)
+    rt = np.stack([base[i % 6] if i < 6 else synth.jitter_widths(base[i % 6], 900 + i) for i in range(B)])
+    # instances 12..17: rotated + translated copies of 0..5 ; 18..23: reversed direction copies of 0..5
+    c, s = np.cos(1.1), np.sin(1.1)
+    R = np.array([[c, -s], [s, c]])
+    for i in range(6):
+        rt[12 + i] = rt[i]
+        rt[12 + i, :, :2] = rt[i, :, :2] @ R.T + np.array([250.0, -75.0])
+        idx = np.r_[0, np.arange(n - 1, 0, -1)]
+        rt[18 + i] = rt[i][idx][:, [0, 1, 3, 2]]
+    rtd = torch.tensor(rt, device=dev)
+    cx, cy, nv, h = B_.calc_splines_batch(rtd)
+    res = B_.opt_min_curv_batch(rtd, nv, h, 0.12, 2.0)
+    assert int((res["status"] != 0).sum()) == 0
+    al = res["alpha"].cpu().numpy()
+    assert res["iters"].max().item() <= 25
+    for i in range(6):
+        assert rel_max(al[12 + i], al[i]) <= 1e-6                 # rigid motion invariance
+        idx = np.r_[0, np.arange(n - 1, 0, -1)]
+        assert rel_max(-al[18 + i][idx], al[i]) <= 5e-3           # reversal: same curve, mirrored knots
+    # KKT check against the kernel's own band (slab layout mirrors csrc/mincurv_ws.cuh)
+    ws = [v for k, v in B_._WS.items() if k[0] == "mincurv"][0].view(torch.float64)
+    NUM_VEC, HB_PITCH, ZB_PITCH = 40, 34, 74
+    np_ = ((n + 31) // 32) * 32 + 64
+    nb_max = (n - 32 + 31) // 32
+    o_hb = NUM_VEC * np_ + n * ZB_PITCH
+    stride = ((o_hb + np_ * HB_PITCH + (3 * nb_max + 1) * 1024) + 15) & ~15
+    V = "H DIAG DFW DBW LFW INVD TII RHOP RHOM PX PY NX NY MX MY XP YP SX SY KREF LB UB F".split()
+    for b in range(0, B, 5):
+        slab = ws[b * stride:(b + 1) * stride].cpu().numpy()
+        HB = slab[o_hb:o_hb + np_ * HB_PITCH].reshape(-1, HB_PITCH)[:n, :33]
+        f = slab[V.index("F") * np_:][:n]
+        lb, ub = slab[V.index("LB") * np_:][:n], slab[V.index("UB") * np_:][:n]
+        a = al[b]
+        Ha = HB[:, 0] * a
+        for k in range(1, 33):
+            Ha += HB[:, k] * np.roll(a, -k) + np.roll(HB[:, k] * a, k)
+        grad = Ha + f
+        scale = np.abs(f).max()
+        assert np.all(a <= ub + 1e-9) and np.all(a >= lb - 1e-9)
+        at_ub, at_lb = (ub - a) < 1e-7, (a - lb) < 1e-7
+        free = ~(at_ub | at_lb)
+        assert np.abs(grad[free]).max() <= 1e-6 * scale
+        assert np.all(grad[at_ub] <= 1e-6 * scale) and np.all(grad[at_lb] >= -1e-6 * scale)
+
+
+def test_raceline_batch_properties_at_baseline_size():
+    dev = torch.device("cuda")
+    n, B = 1000, 8
+    rt = torch.tensor(synth.make_batch(700, B, n), device=dev)
+    cx, cy, nv, h = B_.calc_splines_batch(rt)
+    res = B_.opt_min_curv_batch(rt, nv, h, 0.12, 2.0)
+    rl = B_.create_raceline_batch(rt, nv, res["alpha"], 2.0)
+    no = rl["n_out"].cpu().numpy()
+    assert np.all(no > 0)
+    for b in range(B):
+        m = int(no[b])
+        s = rl["s_interp"][b, :m].cpu().numpy()
+        el = rl["el_lengths_interp"][b, :m].cpu().numpy()
+        L = float(rl["spline_lengths"][b].sum())
+        assert np.all(np.diff(s) > 0) and abs(s[-1] + el[-1] - L) < 1e-8      # equidistant stations close the lap
+        assert abs(el[:-1].std()) < 1e-9 and m == int(np.ceil(L / 2.0))
+        t = rl["t_values"][b, :m].cpu().numpy()
+        assert np.all((t >= 0) & (t < 1.0 + 1e-12))
+        ind = rl["spline_inds"][b, :m].cpu().numpy()
+        assert np.all(np.diff(ind) >= 0) and ind[-1] <= n - 1
+        xy = rl["raceline_interp"][b, :m].cpu().numpy()
+        d = np.linalg.norm(np.diff(xy, axis=0), axis=1)
+        assert np.abs(d - el[:-1]).max() < 2e-3                              # chord ~ arc at 2 m steps
+        kap = rl["kappa"][b, :m].cpu().numpy()
+        assert np.abs(kap).max() < 0.5

@@ -16,14 +16,14 @@ dev = torch.device("cuda")
 rep = {}
 
 def layout(n_max):
-    NUM_VEC = 38; ZB_PITCH = 74; HB_PITCH = 34
+    NUM_VEC = 40; ZB_PITCH = 74; HB_PITCH = 34
     np_ = ((n_max + 31) // 32) * 32 + 64
     nb_max = max(1, (n_max - 32 + 31) // 32)
     o = NUM_VEC * np_; o_zb = o; o += n_max * ZB_PITCH; o_hb = o; o += np_ * HB_PITCH; o_t = o; o += (3 * nb_max + 1) * 1024
     stride = (o + 15) & ~15
     return dict(np=np_, o_zb=o_zb, o_hb=o_hb, o_tiles=o_t, stride=stride, nb_max=nb_max)
 
-VEC = "H DIAG DFW DBW LFW INVD TII RHOP RHOM PX PY NX NY MX MY XP YP SX SY KREF LB UB F T0 T1 T2 T3 T4 T5 ALPHA LU LL RD RHS DX DD DLU DLL".split()
+VEC = "H DIAG DFW DBW LFW INVD TII RHOP RHOM PX PY NX NY MX MY XP YP SX SY KREF LB UB F T0 T1 T2 T3 T4 T5 ALPHA LU LL RD RHS DX DD DLU DLL SU SL".split()
 
 for N in [128, 200, 333]:
     rt = synth.make_track(1, N)
@@ -75,6 +75,6 @@ for Bn, N in [(64, 1000), (592, 1000)]:
         res = B_.opt_min_curv_batch(rtd, nvd, hd, 0.12, 2.0)
         torch.cuda.synchronize(); dt = time.time() - t0
     st = res["status"].cpu().numpy(); it = res["iters"].cpu().numpy()
-    print("timing", Bn, N, f"{dt*1e3:.1f} ms", f"{Bn/dt:.0f} QP/s", "status", np.bincount(st[st >= 0], minlength=5).tolist(), "iters", it.min(), it.mean(), it.max(), flush=True)
+    fail = np.nonzero(st == 3)[0]; print("fail idx", fail[:8], "iters at fail", it[fail][:8]); print("timing", Bn, N, f"{dt*1e3:.1f} ms", f"{Bn/dt:.0f} QP/s", "status", np.bincount(st[st >= 0], minlength=5).tolist(), "iters", it.min(), it.mean(), it.max(), flush=True)
     rep[f"timing_{Bn}_{N}"] = dict(ms=dt * 1e3, qps=Bn / dt, iters_mean=float(it.mean()))
 json.dump(rep, open(os.path.join(OUT, "gpu_check.json"), "w"), indent=1, default=str)
