@@ -52,7 +52,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         try:
@@ -68,7 +68,7 @@ class ClockSampler(threading.Thread):
                      const("nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"): "sw_power_cap"}
             get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
                 getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
-            while not self._stop.is_set():
+            while not self._halt.is_set():
                 self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 r = get_reasons(h)
                 for bit, nm in names.items():
@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
             self.reasons.add(f"sampler_error:{type(e).__name__}")
 
     def stop(self) -> dict:
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons)}

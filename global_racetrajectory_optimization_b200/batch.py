@@ -30,6 +30,25 @@ STATUS_TEXT = {
 
 _WS = {}
 
+# mirror of csrc/mincurv_ws.cuh (debugging / tests read intermediate results out of the workspace)
+SLAB_VECTORS = ("H DIAG DFW DBW LFW INVD TII RHOP RHOM PX PY NX NY MX MY XP YP SX SY KREF LB UB F "
+                "T0 T1 T2 T3 T4 T5 ALPHA LU LL RD RHS DX DD DLU DLL SU SL").split()
+HB_PITCH = 34
+ZB_PITCH = 106
+
+
+def mincurv_slab_layout(n_max: int) -> dict:
+    np_ = ((n_max + 31) // 32) * 32 + 64
+    nb_max = max(1, (n_max - 32 + 31) // 32)
+    o = len(SLAB_VECTORS) * np_
+    o_zb = o
+    o += n_max * ZB_PITCH
+    o_hb = o
+    o += np_ * HB_PITCH
+    o_tiles = o
+    o += (3 * nb_max + 1) * 1024
+    return dict(np=np_, nb_max=nb_max, o_zb=o_zb, o_hb=o_hb, o_tiles=o_tiles, stride=(o + 15) & ~15)
+
 
 def _require_cuda() -> None:
     if not torch.cuda.is_available():

@@ -2,109 +2,69 @@
 // predictor-corrector primal-dual interior-point method (replaces quadprog.solve_qp inside
 // tph.opt_min_curv, call site /root/reference/main_globaltraj.py:264-271).
 //
-// One CTA of two warps per QP instance.  H is the cyclic band (half-bandwidth 32) assembled by K2a.
+// One CTA of four warps per QP instance.  H is the cyclic band (half-bandwidth 32) assembled by K2a.
 // Every interior-point iteration factorises M = H + D (D diagonal, from the barrier) with a
 // block-cyclic Cholesky on 32x32 blocks:
 //   chain blocks I = 0..nb-1 (nodes 0..n-33, padded), separator S = last 32 nodes (closes the cycle)
-//     A'_I   = A_I + D_I - T_I T_I^T                 T_I   = L_{I,I-1}
+//     A'_I   = A_I + D_I - T_I T_I^T                 T_I   = L_{I,I-1}      (upper triangular)
 //     L_II   = chol(A'_I),  Linv_I = L_II^{-1}       (explicit inverse: sweeps become mat-vecs)
 //     T_{I+1}= B_I Linv_I^T                          B_I   = M[block I+1, block I]
 //     F_I    = (Y_I - F_{I-1} T_I^T) Linv_I^T        Y_I   = M[S, block I]   (fill row of the separator)
 //     S     -= F_I F_I^T
-// warp 0 owns the chain (A', chol, inverse, T), warp 1 owns the separator row (F, S); both keep one
-// 32-entry row per lane in registers and read the other operand as broadcast from swizzled
-// shared-memory tiles.  Tiles of the factor (Linv_I, T_I, F_I) go to the instance's HBM slab in
-// column-major 8 KB tiles; the triangular sweeps are sequences of 32x32 mat-vecs over them.
+// The 32x32x32 block products are dense fp64 contractions and run on the FP64 tensor cores
+// (mma.sync.m8n8k4.f64, SASS DMMA) on 8x8 sub-blocks, skipping the sub-blocks that the triangular
+// structure of T / Linv makes zero (40 instead of 128 DMMA for the chain products).  The sequential parts
+// (32x32 Cholesky, triangular inverse) are rolled loops over shared-memory tiles, which keeps the whole
+// kernel inside the instruction cache (the first, fully unrolled version of this kernel was 442 KB of
+// SASS and instruction-fetch bound: profiles/r01_v1_pdip_ncu_summary.json).
+// warp 0 owns the chain (A', chol, inverse, T); warps 1/2 own the two 16-row halves of the separator row
+// (F, S); warp 3 stages the band rows of the next block.  The factor goes to the instance's HBM slab as one
+// packed 32x33 tile per block (Linv_I lower | T_I upper) plus one 32x32 tile F_I; the triangular sweeps
+// are sequences of 32x32 mat-vecs over them.
 #include "mincurv_ws.cuh"
 
 namespace mc {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int PD_THREADS = 64;
+constexpr int PD_THREADS = 128;
+constexpr int TP = 36;             // shared tile pitch (doubles): conflict-free DMMA fragment loads
+constexpr int LTP = 33;            // pitch of the packed (Linv | T) tile in HBM
+constexpr int LT_TILE = 32 * LTP;  // 1056 doubles
+constexpr int F_TILE = 32 * LTP;   // F_I, row-major pitch 33 (odd pitch: conflict-free lane=row and lane=column access)
+constexpr int BLK_TILES = LT_TILE + F_TILE;   // doubles per chain block in the slab (one contiguous bulk copy)
+constexpr unsigned BLK_BYTES = BLK_TILES * sizeof(double);
+constexpr unsigned LT_BYTES = LT_TILE * sizeof(double);
 
-// 32x32 shared tile, row-major with a 16-byte pair swizzle: conflict-free for "lane = row" vector stores
-// and for broadcast pair loads with compile-time (row, pair).
-__device__ __forceinline__ int tidx(int r, int k) { return r * 32 + 2 * ((k >> 1) ^ (r & 15)) + (k & 1); }
-__device__ __forceinline__ double2 tpair(const double *t, int r, int p) {
-    return *reinterpret_cast<const double2 *>(t + r * 32 + 2 * (p ^ (r & 15)));
-}
-// store this lane's row x[0..31] as row `lane` of tile t
-__device__ __forceinline__ void tile_store_row(double *t, const double (&x)[32], int lane) {
-#pragma unroll
-    for (int p = 0; p < 16; ++p)
-        *reinterpret_cast<double2 *>(t + lane * 32 + 2 * (p ^ (lane & 15))) = make_double2(x[2 * p], x[2 * p + 1]);
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// acc[c] -= sum_k x[k] * Y[c][k]   (C -= X Y^T, X rows in registers, Y broadcast from shared)
-__device__ __forceinline__ void gemm_sub_xyT(double (&acc)[32], const double (&x)[32], const double *Y) {
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int p = 0; p < 16; ++p) {
-            const double2 y = tpair(Y, c, p);
-            s0 = fma(x[2 * p], y.x, s0);
-            s1 = fma(x[2 * p + 1], y.y, s1);
-        }
-        acc[c] -= (s0 + s1);
+// ---- TMA (bulk async copy) + mbarrier helpers: the triangular sweeps stream the factor tiles HBM -> shared ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     }
 }
-// out[c] = sum_{k <= c} x[k] * Y[c][k]   (X Y^T with Y lower triangular); in place (descending c)
-__device__ __forceinline__ void trmm_inplace_xLT(double (&x)[32], const double *Y) {
-#pragma unroll
-    for (int c = 31; c >= 0; --c) {
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int p = 0; p <= (c >> 1); ++p) {
-            const double2 y = tpair(Y, c, p);
-            s0 = fma(x[2 * p], y.x, s0);
-            if (2 * p + 1 <= c) s1 = fma(x[2 * p + 1], y.y, s1);
-        }
-        x[c] = s0 + s1;
-    }
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Cholesky of a 32x32 SPD block, one row per lane (entries c <= lane meaningful).
-// On exit a[c] = L[lane][c] for c <= lane (entries c > lane are garbage). lcol: 32 doubles of shared.
-__device__ __forceinline__ bool chol32(double (&a)[32], double *lcol, int lane) {
-    bool ok = true;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-        const double d = __shfl_sync(FULL, a[k], k);
-        if (!(d > 0.0)) ok = false;
-        const double l = a[k] * rsqrt(d);
-        a[k] = l;
-        lcol[lane] = l;
-        __syncwarp();
-#pragma unroll
-        for (int c = k + 1; c < 32; ++c) a[c] = fma(-l, lcol[c], a[c]);
-        __syncwarp();
-    }
-    return ok;
-}
-
-// lane c computes column c of L^{-1}: x[r] = Linv[r][c].  Ls: swizzled tile of L (lower part valid),
-// dinv[r] = 1 / L[r][r] (shared).
-__device__ __forceinline__ void trinv32(double (&x)[32], const double *Ls, const double *dinv, int lane) {
-#pragma unroll
-    for (int r = 0; r < 32; ++r) {
-        double s0 = (r == lane) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-        for (int p = 0; p < (r + 1) / 2; ++p) {
-            const double2 y = tpair(Ls, r, p);
-            if (p & 1) {
-                s2 = fma(-y.x, x[2 * p], s2);
-                if (2 * p + 1 < r) s3 = fma(-y.y, x[2 * p + 1], s3);
-            } else {
-                s0 = fma(-y.x, x[2 * p], s0);
-                if (2 * p + 1 < r) s1 = fma(-y.y, x[2 * p + 1], s1);
-            }
-        }
-        x[r] = ((s0 + s1) + (s2 + s3)) * dinv[r];
-    }
-}
-
-// entry M[i][j] of the cyclic band (real node indices, i != j allowed in any order), 0 outside the band
+// entry M[i][j] of the cyclic band (real node indices), 0 outside the band
 __device__ __forceinline__ double hentry(const double *HB, int n, int i, int j) {
     int k = j - i;
     if (k < 0) k += n;
@@ -115,266 +75,500 @@ __device__ __forceinline__ double hentry(const double *HB, int n, int i, int j) 
 }
 
 struct PdShared {
-    double band[32 * HB_PITCH];   // band rows of the current chain block
-    double Ls[1024];              // L_II (swizzled)
-    double Li[1024];              // Linv_I (swizzled, row-major: Li[c][k] = Linv[c][k])
-    double Ts[1024];              // T_I = L_{I,I-1} (swizzled)
-    double Fs[1024];              // F_I (swizzled)
-    double Ss[1024];              // separator Schur complement, Ss[c * 32 + lane] = S[lane][c]
-    double lcol[2][32];
+    double band[2][32 * HB_PITCH];   // band rows of the current / next chain block
+    // The five factorisation tiles; during the triangular sweeps the same 46 KB hold the two 16.5 KB
+    // staging buffers of the TMA tile pipeline (stage s at &As[0] + s * BLK_TILES).
+    double As[32 * TP];              // A'_I -> L_II, column-major: As[c * TP + r]
+    double Li[32 * TP];              // Linv_I, row-major
+    double Ts[32 * TP];              // T_I, row-major (upper triangular)
+    double Fa[32 * TP];              // F tiles, ping
+    double Fb[32 * TP];              // pong
+    uint64_t full_bar[2], empty_bar[2];
     double dinv[32];
-    double vbuf[4][32];
+    double vbuf[8][32];
     double red[32];
     int flag;
 };
 
+// 32x32 Cholesky, lane = row, tile column-major in shared (As[c*TP + r]); in place, lower triangle only.
+// Left-looking over four 8-column panels: the contributions of the finished columns are subtracted with
+// eight independent accumulators (rolled loop, two broadcast LDS.128 + one LDS per step), then the 8-column
+// panel is factored in registers with warp shuffles.  Also writes dinv[r] = 1 / L[r][r].
+__device__ __forceinline__ bool chol32_smem(double *As, double *dinv, int lane) {
+    bool ok = true;
+#pragma unroll 1
+    for (int J = 0; J < 4; ++J) {
+        const int c0 = 8 * J;
+        double a[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) a[t] = As[(c0 + t) * TP + lane];
+#pragma unroll 2
+        for (int j = 0; j < c0; ++j) {
+            const double lr = -As[j * TP + lane];
+            const double2 b0 = *reinterpret_cast<const double2 *>(&As[j * TP + c0]);
+            const double2 b1 = *reinterpret_cast<const double2 *>(&As[j * TP + c0 + 2]);
+            const double2 b2 = *reinterpret_cast<const double2 *>(&As[j * TP + c0 + 4]);
+            const double2 b3 = *reinterpret_cast<const double2 *>(&As[j * TP + c0 + 6]);
+            a[0] = fma(lr, b0.x, a[0]); a[1] = fma(lr, b0.y, a[1]);
+            a[2] = fma(lr, b1.x, a[2]); a[3] = fma(lr, b1.y, a[3]);
+            a[4] = fma(lr, b2.x, a[4]); a[5] = fma(lr, b2.y, a[5]);
+            a[6] = fma(lr, b3.x, a[6]); a[7] = fma(lr, b3.y, a[7]);
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const double d = __shfl_sync(FULL, a[t], c0 + t);
+            if (!(d > 0.0)) ok = false;
+            const double rs = rsqrt(d);
+            const double l = a[t] * rs;
+            a[t] = l;
+#pragma unroll
+            for (int u = t + 1; u < 8; ++u) a[u] = fma(-l, __shfl_sync(FULL, l, c0 + u), a[u]);
+            if (lane == c0 + t) dinv[c0 + t] = rs;
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+            if (lane >= c0 + t) As[(c0 + t) * TP + lane] = a[t];
+        __syncwarp();
+    }
+    return ok;
+}
+
+// Linv = L^{-1}: lane = column c; L column-major in As, Linv row-major in Li (full tile written, zeros above the
+// diagonal).  Four 8-row panels: contributions of the finished rows with eight independent accumulators, then
+// the 8x8 triangular solve of the panel.
+__device__ __forceinline__ void trinv32_smem(const double *As, const double *dinv, double *Li, int lane) {
+#pragma unroll 1
+    for (int R = 0; R < 4; ++R) {
+        const int r0 = 8 * R;
+        double sacc[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) sacc[t] = (r0 + t == lane) ? 1.0 : 0.0;
+#pragma unroll 2
+        for (int k = 0; k < r0; ++k) {
+            const double x = -Li[k * TP + lane];
+            const double2 b0 = *reinterpret_cast<const double2 *>(&As[k * TP + r0]);
+            const double2 b1 = *reinterpret_cast<const double2 *>(&As[k * TP + r0 + 2]);
+            const double2 b2 = *reinterpret_cast<const double2 *>(&As[k * TP + r0 + 4]);
+            const double2 b3 = *reinterpret_cast<const double2 *>(&As[k * TP + r0 + 6]);
+            sacc[0] = fma(b0.x, x, sacc[0]); sacc[1] = fma(b0.y, x, sacc[1]);
+            sacc[2] = fma(b1.x, x, sacc[2]); sacc[3] = fma(b1.y, x, sacc[3]);
+            sacc[4] = fma(b2.x, x, sacc[4]); sacc[5] = fma(b2.y, x, sacc[5]);
+            sacc[6] = fma(b3.x, x, sacc[6]); sacc[7] = fma(b3.y, x, sacc[7]);
+        }
+        double xv[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            double acc = sacc[t];
+#pragma unroll
+            for (int u = 0; u < t; ++u) acc = fma(-As[(r0 + u) * TP + r0 + t], xv[u], acc);
+            xv[t] = acc * dinv[r0 + t];
+            Li[(r0 + t) * TP + lane] = xv[t];
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // factorisation of M = H + diag(DD); returns false on a non-positive pivot
 // ------------------------------------------------------------------------------------------------
-__device__ bool factor(PdShared &sh, const double *__restrict__ HB, const double *__restrict__ DD,
+__device__ __noinline__ bool factor(PdShared &sh, const double *__restrict__ HB, const double *__restrict__ DD,
                        double *__restrict__ tiles, int n, int nb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
     const int NA = n - 32;
     bool ok = true;
-    double t[32];    // warp 0: row `lane` of T_I ; warp 1: row `lane` of F_{I-1}
-#pragma unroll
-    for (int c = 0; c < 32; ++c) t[c] = 0.0;
+    double sacc[2][4][2];          // warps 1,2: their 16 rows of the separator Schur complement (C fragments)
+    double *Fcur = sh.Fa, *Fnxt = sh.Fb;
 
-    if (warp == 1) {   // separator diagonal block C + D
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            double v = hentry(HB, n, NA + lane, NA + c);
-            if (c == lane) v += DD[NA + lane];
-            sh.Ss[c * 32 + lane] = v;
-        }
+    // separator diagonal block C + D_S: gathered into As by all threads, then picked up as C fragments
+#pragma unroll 1
+    for (int e = threadIdx.x; e < 1024; e += PD_THREADS) {
+        const int r = e >> 5, c = e & 31;
+        double v = hentry(HB, n, NA + r, NA + c);
+        if (r == c) v += DD[NA + r];
+        sh.As[c * TP + r] = v;
     }
+    __syncthreads();
+    if (warp == 1 || warp == 2) {
+        const int ib = 2 * (warp - 1);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) sacc[i][j][e] = sh.As[(8 * j + 2 * q + e) * TP + 8 * (ib + i) + g];
+    }
+    __syncthreads();
+    // stage the band rows of block 0
+    for (int e = threadIdx.x; e < 32 * HB_PITCH; e += PD_THREADS) sh.band[0][e] = HB[e];
+    __syncthreads();
 
     for (int I = 0; I < nb; ++I) {
         const int base = 32 * I;
-        // ---- stage the band rows of block I (coalesced) ----
-        __syncthreads();
-        for (int e = threadIdx.x; e < 32 * HB_PITCH; e += PD_THREADS) {
-            const int row = base + e / HB_PITCH;
-            sh.band[e] = (row < n) ? HB[(size_t)base * HB_PITCH + e] : 0.0;
-        }
-        __syncthreads();
+        const double *band = sh.band[I & 1];
         // =========================== phase A ===========================
         if (warp == 0) {
-            double a[32];
-            const int node = base + lane;
-            const bool real = node < NA;
-            // m1: row `lane` of A_I + D_I (lower part incl. diagonal is what chol32 needs; fill all)
-            const double dd = real ? DD[node] : 0.0;
+            // ---- A' = A_I + D_I - T_I T_I^T (lower 8x8 blocks), written column-major into As ----
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const int lo = (c < lane) ? c : lane, dist = (c < lane) ? lane - c : c - lane;
-                double v = sh.band[lo * HB_PITCH + dist];
-                const bool creal = (base + c) < NA;
-                if (!(real && creal)) v = (c == lane) ? 1.0 : 0.0;
-                else if (c == lane) v += dd;
-                a[c] = v;
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    double c2[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int r = 8 * i + g, c = 8 * j + 2 * q + e;
+                        const int lo = (c < r) ? c : r, dist = (c < r) ? r - c : c - r;
+                        double v = band[lo * HB_PITCH + dist];
+                        const bool real = (base + r) < NA && (base + c) < NA;
+                        if (!real) v = (r == c) ? 1.0 : 0.0;
+                        else if (r == c) v += DD[base + r];
+                        c2[e] = v;
+                    }
+                    if (I > 0) {
+                        double m2[2] = {0.0, 0.0};
+#pragma unroll
+                        for (int K = i; K < 4; ++K)      // T upper triangular: blocks (i,K), (j,K) nonzero for K >= i >= j
+#pragma unroll
+                            for (int s = 0; s < 2; ++s)
+                                dmma(m2, sh.Ts[(8 * i + g) * TP + 8 * K + 4 * s + q], sh.Ts[(8 * j + g) * TP + 8 * K + 4 * s + q]);
+                        c2[0] -= m2[0];
+                        c2[1] -= m2[1];
+                    }
+                    sh.As[(8 * j + 2 * q) * TP + 8 * i + g] = c2[0];
+                    sh.As[(8 * j + 2 * q + 1) * TP + 8 * i + g] = c2[1];
+                }
             }
-            // m2: A' = A - T_I T_I^T
-            if (I > 0) gemm_sub_xyT(a, t, sh.Ts);
-            // m3: Cholesky
-            ok = chol32(a, sh.lcol[0], lane) && ok;
-            // m4: L_II -> shared (zero the strict upper part)
-#pragma unroll
-            for (int c = 0; c < 32; ++c) if (c > lane) a[c] = 0.0;
-            tile_store_row(sh.Ls, a, lane);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) if (c == lane) sh.dinv[lane] = 1.0 / a[c];
             __syncwarp();
-            // m5: explicit inverse, lane = column
-            double xi[32];
-            trinv32(xi, sh.Ls, sh.dinv, lane);
-            // Linv -> shared row-major (Li[r][lane] = xi[r]) and HBM tile (column-major: [lane*32 + r])
-            double *gt = tiles + (size_t)(3 * I + 0) * 1024 + lane * 32;
-#pragma unroll
-            for (int r = 0; r < 32; ++r) sh.Li[tidx(r, lane)] = xi[r];
-#pragma unroll
-            for (int r = 0; r < 32; r += 2) *reinterpret_cast<double2 *>(gt + r) = make_double2(xi[r], xi[r + 1]);
+            ok = chol32_smem(sh.As, sh.dinv, lane) && ok;
+            trinv32_smem(sh.As, sh.dinv, sh.Li, lane);
+        } else if (warp == 3) {
+            if (I + 1 < nb) {      // stage the band rows of the next block
+                double *dst = sh.band[(I + 1) & 1];
+                const double *src = HB + (size_t)(base + 32) * HB_PITCH;
+                for (int e = lane; e < 32 * HB_PITCH; e += 32) dst[e] = src[e];
+            }
         } else {
-            // f4 (previous block): S -= F_{I-1} F_{I-1}^T
+            const int ib = 2 * (warp - 1);
+            // ---- S -= F_{I-1} F_{I-1}^T (own 16 rows) ----
             if (I > 0) {
-                double s[32];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) s[c] = sh.Ss[c * 32 + lane];
-                gemm_sub_xyT(s, t, sh.Fs);
+                for (int K = 0; K < 4; ++K)
 #pragma unroll
-                for (int c = 0; c < 32; ++c) sh.Ss[c * 32 + lane] = s[c];
+                    for (int s = 0; s < 2; ++s) {
+                        double a[2], b[4];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) a[i] = -Fcur[(8 * (ib + i) + g) * TP + 8 * K + 4 * s + q];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) b[j] = Fcur[(8 * j + g) * TP + 8 * K + 4 * s + q];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) dmma(sacc[i][j], a[i], b[j]);
+                    }
             }
-            // f2: FW = Y_I - F_{I-1} T_I^T   (Y_I nonzero only next to the separator / across the wrap)
-            double fw[32];
+            // ---- FW = Y_I - F_{I-1} T_I^T (own rows) -> Fnxt ----
             const bool hasY = (I == 0) || (base + 31 >= NA - 32);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                double v = 0.0;
-                if (hasY && (base + c) < NA) v = hentry(HB, n, NA + lane, base + c);
-                fw[c] = v;
+            if (hasY) {      // Y_I = M[S, block I] is nonzero only across the wrap (I = 0) and next to the separator
+#pragma unroll 1
+                for (int e = lane; e < 512; e += 32) {
+                    const int r = 16 * (warp - 1) + (e >> 5), c = e & 31;
+                    Fnxt[r * TP + c] = ((base + c) < NA) ? hentry(HB, n, NA + r, base + c) : 0.0;
+                }
+                __syncwarp();
             }
-            if (I > 0) gemm_sub_xyT(fw, t, sh.Ts);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) t[c] = fw[c];
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    double c2[2] = {0.0, 0.0};
+                    if (hasY) {
+                        const double2 y2 = *reinterpret_cast<const double2 *>(&Fnxt[(8 * (ib + i) + g) * TP + 8 * j + 2 * q]);
+                        c2[0] = y2.x;
+                        c2[1] = y2.y;
+                    }
+                    if (I > 0) {
+                        double m2[2] = {0.0, 0.0};
+#pragma unroll
+                        for (int K = j; K < 4; ++K)      // T[c][k] != 0 for k >= c
+#pragma unroll
+                            for (int s = 0; s < 2; ++s)
+                                dmma(m2, Fcur[(8 * (ib + i) + g) * TP + 8 * K + 4 * s + q], sh.Ts[(8 * j + g) * TP + 8 * K + 4 * s + q]);
+                        c2[0] -= m2[0];
+                        c2[1] -= m2[1];
+                    }
+                    __syncwarp();
+                    *reinterpret_cast<double2 *>(&Fnxt[(8 * (ib + i) + g) * TP + 8 * j + 2 * q]) = make_double2(c2[0], c2[1]);
+                }
         }
         __syncthreads();
         // =========================== phase B ===========================
         if (warp == 0) {
+            // Linv_I -> packed HBM tile (lower part, row-major pitch 33)
+            double *gt = tiles + (size_t)I * BLK_TILES;
+            for (int r = 0; r < 32; ++r)
+                if (lane <= r) gt[r * LTP + lane] = sh.Li[r * TP + lane];
             if (I + 1 < nb) {
-                // m6: T_{I+1} = B_I Linv_I^T, B_I[r][k] = M[base+32+r][base+k] = band[k][32 + r - k] (r <= k)
-                const bool real = (base + 32 + lane) < NA;
+                // ---- T_{I+1} = B_I Linv_I^T : upper-triangular blocks (i <= j), K = i..j ----
+                double *gn = tiles + (size_t)(I + 1) * BLK_TILES;
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    double v = 0.0;
-                    if (lane <= k && real) v = sh.band[k * HB_PITCH + 32 + lane - k];
-                    t[k] = v;
-                }
-                trmm_inplace_xLT(t, sh.Li);
-                double *gt = tiles + (size_t)(3 * (I + 1) + 1) * 1024;
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int c = 0; c < 32; ++c) gt[c * 32 + lane] = t[c];
-                // Ts is only read in phase A: safe to publish T_{I+1} now
-                tile_store_row(sh.Ts, t, lane);
+                    for (int j = 0; j < 4; ++j) {
+                        double c2[2] = {0.0, 0.0};
+                        if (j >= i) {
+#pragma unroll
+                            for (int K = i; K <= j; ++K)
+#pragma unroll
+                                for (int s = 0; s < 2; ++s) {
+                                    // B_I[r][k] = M[base+32+r][base+k] = band[k][32 + r - k] for r <= k
+                                    const int r = 8 * i + g, k = 8 * K + 4 * s + q;
+                                    double a = 0.0;
+                                    if (r <= k && (base + 32 + r) < NA) a = band[k * HB_PITCH + 32 + r - k];
+                                    dmma(c2, a, sh.Li[(8 * j + g) * TP + k]);
+                                }
+                        }
+                        const int r = 8 * i + g, c = 8 * j + 2 * q;
+                        *reinterpret_cast<double2 *>(&sh.Ts[r * TP + c]) = make_double2(c2[0], c2[1]);
+                        if (c >= r) gn[r * LTP + c + 1] = c2[0];
+                        if (c + 1 >= r) gn[r * LTP + c + 2] = c2[1];
+                    }
             }
-        } else {
-            // f3: F_I = FW Linv_I^T (in place in t)
-            trmm_inplace_xLT(t, sh.Li);
-            double *gt = tiles + (size_t)(3 * I + 2) * 1024;
+        } else if (warp == 1 || warp == 2) {
+            const int ib = 2 * (warp - 1);
+            // ---- F_I = FW Linv_I^T (own rows; Linv lower triangular: K <= j), in place in Fnxt ----
+            double a[2][8];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) gt[c * 32 + lane] = t[c];
-            tile_store_row(sh.Fs, t, lane);   // Fs is only read in phase A (by this warp)
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) a[i][ks] = Fnxt[(8 * (ib + i) + g) * TP + 4 * ks + q];
+            __syncwarp();
+            double *gf = tiles + (size_t)I * BLK_TILES + LT_TILE;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    double c2[2] = {0.0, 0.0};
+#pragma unroll
+                    for (int K = 0; K <= j; ++K)
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) dmma(c2, a[i][2 * K + s], sh.Li[(8 * j + g) * TP + 8 * K + 4 * s + q]);
+                    const int r = 8 * (ib + i) + g, c = 8 * j + 2 * q;
+                    *reinterpret_cast<double2 *>(&Fnxt[r * TP + c]) = make_double2(c2[0], c2[1]);
+                    gf[r * LTP + c] = c2[0];
+                    gf[r * LTP + c + 1] = c2[1];
+                }
         }
+        { double *t = Fcur; Fcur = Fnxt; Fnxt = t; }
+        __syncthreads();
+    }
+    // ---- separator: S -= F_{nb-1} F_{nb-1}^T, handed over through As; chol + inverse by warp 0 ----
+    if (warp == 1 || warp == 2) {
+        const int ib = 2 * (warp - 1);
+#pragma unroll
+        for (int K = 0; K < 4; ++K)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                double a[2], b[4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) a[i] = -Fcur[(8 * (ib + i) + g) * TP + 8 * K + 4 * s + q];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = Fcur[(8 * j + g) * TP + 8 * K + 4 * s + q];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma(sacc[i][j], a[i], b[j]);
+            }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                sh.As[(8 * j + 2 * q) * TP + 8 * (ib + i) + g] = sacc[i][j][0];
+                sh.As[(8 * j + 2 * q + 1) * TP + 8 * (ib + i) + g] = sacc[i][j][1];
+            }
     }
     __syncthreads();
-    // ---- separator: S -= F_{nb-1} F_{nb-1}^T, chol, inverse (warp 1) ----
-    if (warp == 1) {
-        double s[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) s[c] = sh.Ss[c * 32 + lane];
-        gemm_sub_xyT(s, t, sh.Fs);
-        ok = chol32(s, sh.lcol[1], lane) && ok;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) if (c > lane) s[c] = 0.0;
-        tile_store_row(sh.Ls, s, lane);
-#pragma unroll
-        for (int c = 0; c < 32; ++c) if (c == lane) sh.dinv[lane] = 1.0 / s[c];
-        __syncwarp();
-        double xi[32];
-        trinv32(xi, sh.Ls, sh.dinv, lane);
-        double *gt = tiles + (size_t)(3 * nb) * 1024 + lane * 32;
-#pragma unroll
-        for (int r = 0; r < 32; r += 2) *reinterpret_cast<double2 *>(gt + r) = make_double2(xi[r], xi[r + 1]);
+    if (warp == 0) {
+        ok = chol32_smem(sh.As, sh.dinv, lane) && ok;
+        trinv32_smem(sh.As, sh.dinv, sh.Li, lane);
+        double *gt = tiles + (size_t)nb * BLK_TILES;     // separator inverse: row-major pitch 33 (lower part)
+        for (int r = 0; r < 32; ++r)
+            if (lane <= r) gt[r * LTP + lane] = sh.Li[r * TP + lane];
+        if (!ok) sh.flag = 1;
     }
-    if (!ok) sh.flag = 1;
     __syncthreads();
     return sh.flag == 0;
 }
 
-// y = X v (lane = row), X column-major HBM tile, v broadcast from shared
-__device__ __forceinline__ double tile_mv(const double *__restrict__ X, const double *v, int lane) {
+// ---- mat-vecs over one staged block in shared memory: LT = packed (Linv | T), pitch 33; F pitch 33 ----
+// (odd pitch: both "lane = row" and "lane = column" access patterns are bank-conflict free; v is broadcast)
+__device__ __forceinline__ double sm_t_mv(const double *LT, const double *v, int lane) {     // sum_{c >= r} T[r][c] v[c]
+    const double *row = LT + lane * LTP + 1;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
+#pragma unroll 2
     for (int c = 0; c < 32; c += 4) {
-        s0 = fma(X[(c + 0) * 32 + lane], v[c + 0], s0);
-        s1 = fma(X[(c + 1) * 32 + lane], v[c + 1], s1);
-        s2 = fma(X[(c + 2) * 32 + lane], v[c + 2], s2);
-        s3 = fma(X[(c + 3) * 32 + lane], v[c + 3], s3);
+        s0 = fma((c + 0 >= lane) ? row[c + 0] : 0.0, v[c + 0], s0);
+        s1 = fma((c + 1 >= lane) ? row[c + 1] : 0.0, v[c + 1], s1);
+        s2 = fma((c + 2 >= lane) ? row[c + 2] : 0.0, v[c + 2], s2);
+        s3 = fma((c + 3 >= lane) ? row[c + 3] : 0.0, v[c + 3], s3);
     }
     return (s0 + s1) + (s2 + s3);
 }
-// y = X^T v (lane = column of X), X column-major HBM tile: this lane's column is 32 contiguous doubles
-__device__ __forceinline__ double tile_mtv(const double *__restrict__ X, const double *v, int lane) {
-    const double2 *col = reinterpret_cast<const double2 *>(X + lane * 32);
+__device__ __forceinline__ double sm_linv_mv(const double *LT, const double *v, int lane) {  // sum_{c <= r} Linv[r][c] v[c]
+    const double *row = LT + lane * LTP;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-    for (int p = 0; p < 16; p += 2) {
-        const double2 a = col[p], b2 = col[p + 1];
-        s0 = fma(a.x, v[2 * p], s0);
-        s1 = fma(a.y, v[2 * p + 1], s1);
-        s2 = fma(b2.x, v[2 * p + 2], s2);
-        s3 = fma(b2.y, v[2 * p + 3], s3);
+#pragma unroll 2
+    for (int c = 0; c < 32; c += 4) {
+        s0 = fma((c + 0 <= lane) ? row[c + 0] : 0.0, v[c + 0], s0);
+        s1 = fma((c + 1 <= lane) ? row[c + 1] : 0.0, v[c + 1], s1);
+        s2 = fma((c + 2 <= lane) ? row[c + 2] : 0.0, v[c + 2], s2);
+        s3 = fma((c + 3 <= lane) ? row[c + 3] : 0.0, v[c + 3], s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ double sm_linv_mtv(const double *LT, const double *v, int lane) { // sum_{r >= c} Linv[r][c] v[r]
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 2
+    for (int r = 0; r < 32; r += 4) {
+        s0 = fma((r + 0 >= lane) ? LT[(r + 0) * LTP + lane] : 0.0, v[r + 0], s0);
+        s1 = fma((r + 1 >= lane) ? LT[(r + 1) * LTP + lane] : 0.0, v[r + 1], s1);
+        s2 = fma((r + 2 >= lane) ? LT[(r + 2) * LTP + lane] : 0.0, v[r + 2], s2);
+        s3 = fma((r + 3 >= lane) ? LT[(r + 3) * LTP + lane] : 0.0, v[r + 3], s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ double sm_t_mtv(const double *LT, const double *v, int lane) {    // sum_{r <= c} T[r][c] v[r]
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 2
+    for (int r = 0; r < 32; r += 4) {
+        s0 = fma((r + 0 <= lane) ? LT[(r + 0) * LTP + lane + 1] : 0.0, v[r + 0], s0);
+        s1 = fma((r + 1 <= lane) ? LT[(r + 1) * LTP + lane + 1] : 0.0, v[r + 1], s1);
+        s2 = fma((r + 2 <= lane) ? LT[(r + 2) * LTP + lane + 1] : 0.0, v[r + 2], s2);
+        s3 = fma((r + 3 <= lane) ? LT[(r + 3) * LTP + lane + 1] : 0.0, v[r + 3], s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ double sm_f_mv(const double *F, const double *v, int lane) {      // sum_c F[r][c] v[c]
+    const double *row = F + lane * LTP;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 2
+    for (int c = 0; c < 32; c += 4) {
+        s0 = fma(row[c + 0], v[c + 0], s0);
+        s1 = fma(row[c + 1], v[c + 1], s1);
+        s2 = fma(row[c + 2], v[c + 2], s2);
+        s3 = fma(row[c + 3], v[c + 3], s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ double sm_f_mtv(const double *F, const double *v, int lane) {     // sum_r F[r][c] v[r]
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 2
+    for (int r = 0; r < 32; r += 4) {
+        s0 = fma(F[(r + 0) * LTP + lane], v[r + 0], s0);
+        s1 = fma(F[(r + 1) * LTP + lane], v[r + 1], s1);
+        s2 = fma(F[(r + 2) * LTP + lane], v[r + 2], s2);
+        s3 = fma(F[(r + 3) * LTP + lane], v[r + 3], s3);
     }
     return (s0 + s1) + (s2 + s3);
 }
 
 // ------------------------------------------------------------------------------------------------
-// solve M x = g with the stored factor.  g, x: real-indexed vectors (length n) in the slab.
-// ypad / zpad: padded scratch vectors (>= 32 nb + 32 doubles).
+// solve M x = g with the stored factor.  g, x: real-indexed vectors (length n) in the slab; ypad: padded scratch.
+// The 2 nb + 1 factor blocks [0 .. nb-1, S, nb-1 .. 0] are streamed HBM -> shared by one elected thread of
+// warp 3 with cp.async.bulk (TMA, one 16.5 KB copy per block) into a two-stage ring guarded by full/empty
+// mbarriers; warp 0 consumes them: per block three 32x32 mat-vecs from shared memory.
+// `fill` counts the ring fills of this CTA so far (parity bookkeeping); the new count is returned.
 // ------------------------------------------------------------------------------------------------
-__device__ void solve(PdShared &sh, const double *__restrict__ tiles, const double *__restrict__ g,
-                      double *__restrict__ x, double *__restrict__ ypad, double *__restrict__ zpad, int n, int nb) {
+__device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ tiles, const double *__restrict__ g,
+                                       double *__restrict__ x, double *__restrict__ ypad, int n, int nb, unsigned fill) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int NA = n - 32;
-    double *yb = sh.vbuf[0], *tb = sh.vbuf[1], *gs = sh.vbuf[2], *xs = sh.vbuf[3];
+    double *stage0 = sh.As;
+    const unsigned nfill = 2u * nb + 1u;
+    fence_proxy_async();        // the staging area was last written through the generic proxy (factor tiles)
     __syncthreads();
-    // ---- forward chain (warp 0): y_I = Linv_I (g_I - T_I y_{I-1}) ----
-    if (warp == 0) {
+    if (warp == 3) {
+        if (lane == 0) {
+            for (unsigned i = 0; i < nfill; ++i) {
+                const unsigned f = fill + i, st = f & 1u, k = f >> 1;
+                if (k > 0) mbar_wait(&sh.empty_bar[st], (k - 1) & 1u);
+                const unsigned blk = (i < (unsigned)nb) ? i : ((i == (unsigned)nb) ? (unsigned)nb : 2u * nb - i);
+                const unsigned bytes = (i == (unsigned)nb) ? LT_BYTES : BLK_BYTES;
+                mbar_expect_tx(&sh.full_bar[st], bytes);
+                tma_load_1d(stage0 + st * BLK_TILES, tiles + (size_t)blk * BLK_TILES, bytes, &sh.full_bar[st]);
+            }
+        }
+    } else if (warp == 0) {
+        double *yb = sh.vbuf[0], *tb = sh.vbuf[1], *xs = sh.vbuf[3];
+        // ---- forward: y_I = Linv_I (g_I - T_I y_{I-1}),  gS -= F_I y_I ----
+        double gacc = 0.0;
+        double gnext = (lane < NA) ? g[lane] : 0.0;
+        yb[lane] = 0.0;
+        __syncwarp();
         for (int I = 0; I < nb; ++I) {
-            const int node = 32 * I + lane;
-            double v = (node < NA) ? g[node] : 0.0;
-            if (I > 0) v -= tile_mv(tiles + (size_t)(3 * I + 1) * 1024, yb, lane);
+            const unsigned f = fill + I, st = f & 1u, k = f >> 1;
+            const double gv = gnext;
+            if (I + 1 < nb) { const int nd = 32 * (I + 1) + lane; gnext = (nd < NA) ? g[nd] : 0.0; }
+            mbar_wait(&sh.full_bar[st], k & 1u);
+            const double *LT = stage0 + st * BLK_TILES, *Ft = LT + LT_TILE;
+            double v = gv;
+            if (I > 0) v -= sm_t_mv(LT, yb, lane);
             __syncwarp();
             tb[lane] = v;
             __syncwarp();
-            const double y = tile_mv(tiles + (size_t)(3 * I + 0) * 1024, tb, lane);
+            const double y = sm_linv_mv(LT, tb, lane);
             yb[lane] = y;
-            ypad[node] = y;
+            ypad[32 * I + lane] = y;
             __syncwarp();
+            gacc += sm_f_mv(Ft, yb, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.empty_bar[st]);
         }
-    }
-    __syncthreads();
-    // ---- separator right-hand side: gS = g_S - sum_I F_I y_I (both warps, blocks interleaved) ----
-    {
-        double acc = 0.0;
-        for (int I = warp; I < nb; I += 2) {
-            const double *Ft = tiles + (size_t)(3 * I + 2) * 1024;
-            const double *yv = ypad + 32 * I;
-            double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-                s0 = fma(Ft[c * 32 + lane], yv[c], s0);
-                s1 = fma(Ft[(c + 1) * 32 + lane], yv[c + 1], s1);
-            }
-            acc += s0 + s1;
-        }
-        if (warp == 1) tb[lane] = acc;
-        __syncthreads();
-        if (warp == 0) {
-            gs[lane] = g[NA + lane] - acc - tb[lane];
+        // ---- separator: x_S = LinvS^T LinvS (g_S - sum F_I y_I) ----
+        {
+            const unsigned f = fill + nb, st = f & 1u, k = f >> 1;
+            const double gs = g[NA + lane] - gacc;
+            mbar_wait(&sh.full_bar[st], k & 1u);
+            const double *LS = stage0 + st * BLK_TILES;
+            tb[lane] = gs;
             __syncwarp();
-            const double *LS = tiles + (size_t)(3 * nb) * 1024;
-            const double ys = tile_mv(LS, gs, lane);
+            const double ys = sm_linv_mv(LS, tb, lane);
             __syncwarp();
-            tb[lane] = ys;
+            yb[lane] = ys;
             __syncwarp();
-            const double xv = tile_mtv(LS, tb, lane);
+            const double xv = sm_linv_mtv(LS, yb, lane);
             xs[lane] = xv;
             x[NA + lane] = xv;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.empty_bar[st]);
         }
-        __syncthreads();
-    }
-    // ---- z_I = F_I^T x_S for all chain blocks (both warps) ----
-    for (int I = warp; I < nb; I += 2) zpad[32 * I + lane] = tile_mtv(tiles + (size_t)(3 * I + 2) * 1024, xs, lane);
-    __syncthreads();
-    // ---- backward chain (warp 0): x_I = Linv_I^T (y_I - z_I - T_{I+1}^T x_{I+1}) ----
-    if (warp == 0) {
-        for (int I = nb - 1; I >= 0; --I) {
-            const int node = 32 * I + lane;
-            double v = ypad[node] - zpad[node];
-            if (I + 1 < nb) v -= tile_mtv(tiles + (size_t)(3 * (I + 1) + 1) * 1024, yb, lane);
+        // ---- backward: x_I = Linv_I^T (y_I - F_I^T x_S - T_{I+1}^T x_{I+1}) ----
+        double u = 0.0;                               // (T_{I+1}^T x_{I+1})[lane]
+        double ynext = ypad[32 * (nb - 1) + lane];
+        for (int i = 0; i < nb; ++i) {
+            const int I = nb - 1 - i;
+            const unsigned f = fill + nb + 1 + i, st = f & 1u, k = f >> 1;
+            const double yv = ynext;
+            if (I > 0) ynext = ypad[32 * (I - 1) + lane];
+            mbar_wait(&sh.full_bar[st], k & 1u);
+            const double *LT = stage0 + st * BLK_TILES, *Ft = LT + LT_TILE;
+            const double v = yv - sm_f_mtv(Ft, xs, lane) - u;
             __syncwarp();
             tb[lane] = v;
             __syncwarp();
-            const double xv = tile_mtv(tiles + (size_t)(3 * I + 0) * 1024, tb, lane);
+            const double xv = sm_linv_mtv(LT, tb, lane);
             yb[lane] = xv;
-            if (node < NA) x[node] = xv;
+            if (32 * I + lane < NA) x[32 * I + lane] = xv;
             __syncwarp();
+            u = (I > 0) ? sm_t_mtv(LT, yb, lane) : 0.0;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.empty_bar[st]);
         }
     }
     __syncthreads();
+    return fill + nfill;
 }
 
-// banded cyclic mat-vec out = H v (real-indexed), both warps
+// banded cyclic mat-vec out = H v (real-indexed)
 __device__ void band_matvec(const double *__restrict__ HB, const double *__restrict__ v, double *__restrict__ out, int n) {
     for (int i = threadIdx.x; i < n; i += PD_THREADS) {
         const double *row = HB + (size_t)i * HB_PITCH;
@@ -393,12 +587,19 @@ __device__ void band_matvec(const double *__restrict__ HB, const double *__restr
     }
 }
 
-__global__ void __launch_bounds__(PD_THREADS)
+__global__ void __launch_bounds__(PD_THREADS, 3)
 mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double *__restrict__ ws, Layout L,
                     PdipParams prm, double *__restrict__ alpha_out, int32_t *__restrict__ status,
                     int32_t *__restrict__ iters_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PdShared &sh = *reinterpret_cast<PdShared *>(smem_raw);
+    if (threadIdx.x == 0) {
+        mbar_init(&sh.full_bar[0], 1); mbar_init(&sh.full_bar[1], 1);
+        mbar_init(&sh.empty_bar[0], 1); mbar_init(&sh.empty_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned fill = 0;      // ring fills so far (uniform across the CTA)
 
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         const int n = n_pts ? n_pts[b] : n_max;
@@ -416,7 +617,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
         double *AL = vec(slab, L, V_ALPHA), *LU = vec(slab, L, V_LU), *LL = vec(slab, L, V_LL), *RD = vec(slab, L, V_RD);
         double *RHS = vec(slab, L, V_RHS), *DX = vec(slab, L, V_DX), *DD = vec(slab, L, V_DD);
         double *TU = vec(slab, L, V_DLU), *TL = vec(slab, L, V_DLL), *SU = vec(slab, L, V_SU), *SL = vec(slab, L, V_SL);
-        double *YP = vec(slab, L, V_T4), *ZP = vec(slab, L, V_T5), *G0 = vec(slab, L, V_T0);
+        double *YP = vec(slab, L, V_T4), *G0 = vec(slab, L, V_T0);
         const int nb = (n - 32 + 31) / 32;
         if (threadIdx.x == 0) sh.flag = 0;
 
@@ -464,7 +665,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             }
             __syncthreads();
             if (!factor(sh, HB, DD, tiles, n, nb)) { result = 3; break; }
-            solve(sh, tiles, RHS, DX, YP, ZP, n, nb);
+            fill = solve(sh, tiles, RHS, DX, YP, n, nb, fill);
             // ---- affine step lengths, centring parameter ----
             double ap = 1.0, ad = 1.0;
             for (int i = threadIdx.x; i < n; i += PD_THREADS) {
@@ -497,7 +698,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
                 RHS[i] = -RD[i] - tu / su + tl / sl;
             }
             __syncthreads();
-            solve(sh, tiles, RHS, DX, YP, ZP, n, nb);
+            fill = solve(sh, tiles, RHS, DX, YP, n, nb, fill);
             ap = 1e300; ad = 1e300;
             for (int i = threadIdx.x; i < n; i += PD_THREADS) {
                 const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i];

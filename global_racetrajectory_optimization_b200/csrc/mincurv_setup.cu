@@ -7,51 +7,23 @@
 //   T_c q        = h^2 m                                            (A_ex_c A^{-1} q)
 //   T_n{x,y} a   = h^2 Tri^{-1} 6 D2 (n_{x,y} a)   =>  E = S_y Z N_y - S_x Z N_x,  Z = Tri^{-1} 6 D2
 //   H = E^T E (half-bandwidth 32 kept),  f = F_SCALE E^T k_ref,  k_ref = S_y m_y - S_x m_x
-// One CTA per QP instance; O(N) vectors and the Z / H bands live in the instance's HBM slab.
+// The band of H is assembled in O(N b) from the semiseparable structure of Ti = Tri^{-1}
+// (Ti[m][c] = Ti[c][c] prod rho+ for m > c, prod rho- for m < c):
+//   H[i][j]  = ny_i ny_j A0[i][j] - (ny_i nx_j + nx_i ny_j) A1[i][j] + nx_i nx_j A2[i][j]
+//   A_t      = (6 D2)^T B_t (6 D2)                      (9-point stencil, D2 tridiagonal)
+//   B_t[c][c'] = sum_m w_t[m] Ti[m][c] Ti[m][c'],        w = (s_y^2, s_x s_y, s_x^2)
+//              = Ti[c'][c] (Ti[c'][c'] U_t[c'] + Ti[c][c] V_t[c]) + Mid_t(c, c')          (c < c')
+//   U_t[c] = w_t[c] + rho+_{c+1}^2 U_t[c+1],   V_t[c] = w_t[c] + rho-_{c-1}^2 V_t[c-1],
+//   Mid_t(c, c'+1) = rho+_{c'+1} (Mid_t(c, c') + w_t[c'] Ti[c'][c] Ti[c'][c'])
+// (exact sums over all m -- no truncation of E -- verified against the explicit E^T E in tools/).
+// One CTA per QP instance; O(N) vectors and the B / H bands live in the instance's HBM slab.
 #include "mincurv_ws.cuh"
 
 namespace mc {
 
-// band of Z: ZB[m][BZ + o] = Z[m][m + o], o in [-BZ, BZ]; Z[m][i] = 6 (Ti[m][i-1]/h_{i-1}
-//   - Ti[m][i] (1/h_{i-1} + 1/h_i) + Ti[m][i+1]/h_i) with Ti = Tri^{-1} generated outwards from the
-// diagonal by the decay ratios rho+ / rho- (Ti is symmetric: Ti[m][m+o] = Ti[m+o][m]).
-__device__ inline void build_zband(double *zb, const double *h, const double *tii, const double *rhop,
-                                   const double *rhom, int n) {
-    for (int m = threadIdx.x; m < n; m += blockDim.x) {
-        double *row = zb + (size_t)m * ZB_PITCH;
-        const double t0 = tii[m];
-        const int mm1 = (m == 0) ? n - 1 : m - 1;
-        const int mp1 = (m + 1 == n) ? 0 : m + 1;
-        const double tm1 = t0 * rhom[mm1];      // Ti[m][m-1]
-        const double tp1 = t0 * rhop[mp1];      // Ti[m][m+1]
-        {   // o = 0
-            const double him = h[mm1], hi = h[m];
-            row[BZ] = 6.0 * (tm1 / him - t0 * (1.0 / him + 1.0 / hi) + tp1 / hi);
-        }
-        // positive side: i = m + o
-        double tprev = t0, tcur = tp1;
-        int i = mp1;
-        for (int o = 1; o <= BZ; ++o) {
-            const int ip1 = (i + 1 == n) ? 0 : i + 1;
-            const int im1 = (i == 0) ? n - 1 : i - 1;
-            const double tnext = tcur * rhop[ip1];
-            const double him = h[im1], hi = h[i];
-            row[BZ + o] = 6.0 * (tprev / him - tcur * (1.0 / him + 1.0 / hi) + tnext / hi);
-            tprev = tcur; tcur = tnext; i = ip1;
-        }
-        // negative side: i = m - o
-        double tnx = t0;
-        tcur = tm1;
-        i = mm1;
-        for (int o = 1; o <= BZ; ++o) {
-            const int im1 = (i == 0) ? n - 1 : i - 1;
-            const double tpv = tcur * rhom[im1];          // Ti[m][i-1]
-            const double him = h[im1], hi = h[i];
-            row[BZ - o] = 6.0 * (tpv / him - tcur * (1.0 / him + 1.0 / hi) + tnx / hi);
-            tnx = tcur; tcur = tpv; i = im1;
-        }
-    }
-}
+constexpr int BD = 34;               // B_t band: offsets d = c' - c in [0, 34]
+constexpr int BB_T = BD + 1;         // 35 doubles per weight
+static_assert(3 * BB_T <= ZB_PITCH, "B band does not fit the slab pitch");
 
 __global__ void __launch_bounds__(256)
 mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
@@ -81,6 +53,7 @@ mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
     double *SX = vec(slab, L, V_SX), *SY = vec(slab, L, V_SY), *KREF = vec(slab, L, V_KREF);
     double *LB = vec(slab, L, V_LB), *UB = vec(slab, L, V_UB), *F = vec(slab, L, V_F);
     double *T0 = vec(slab, L, V_T0), *T1 = vec(slab, L, V_T1), *T2 = vec(slab, L, V_T2), *T3 = vec(slab, L, V_T3);
+    double *T4 = vec(slab, L, V_T4), *T5 = vec(slab, L, V_T5);
 
     // ---- P1: coalesced, vectorised load of the reftrack rows [x, y, w_r, w_l] (32 B per point) ----
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -121,7 +94,7 @@ mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
     __syncthreads();
     // ---- P4: moments of the reference line ----
     tri_solve2(LFW, INVD, H, T0, T1, T2, T3, MX, MY, n);
-    // ---- P5: linearisation point ----
+    // ---- P5: linearisation point; right-hand sides of f = F_SCALE E^T k_ref ----
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int ip1 = (i + 1 == n) ? 0 : i + 1;
         const double hi = H[i], h2 = hi * hi;
@@ -130,42 +103,106 @@ mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
         const double q = xp * xp + yp * yp;
         const double c = 1.0 / (q * sqrt(q));
         const double sy = c * xp * h2, sx = c * yp * h2;
-        XP[i] = xp; YP[i] = yp; SX[i] = sx; SY[i] = sy;
-        KREF[i] = sy * MY[i] - sx * MX[i];
+        const double kr = sy * MY[i] - sx * MX[i];
+        XP[i] = xp; YP[i] = yp; SX[i] = sx; SY[i] = sy; KREF[i] = kr;
+        T0[i] = sx * kr;
+        T1[i] = sy * kr;
     }
-    // ---- P6: band of Z ----
-    double *ZB = slab + L.o_zb;
-    build_zband(ZB, H, TII, RHOP, RHOM, n);
     __syncthreads();
-    // ---- P7: f = F_SCALE E^T k_ref ----
+    // E^T v = N_y Z^T (S_y v) - N_x Z^T (S_x v),  Z^T = 6 D2 Tri^{-1}
+    tri_solve2(LFW, INVD, H, T0, T1, T2, T3, T4, T5, n);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double nyi = NY[i], nxi = NX[i];
-        double acc = 0.0;
-        int m = wrapi(i - BZ, n);
-        for (int o = BZ; o >= -BZ; --o) {       // m = i - o
-            const double z = ZB[(size_t)m * ZB_PITCH + BZ + o];
-            acc += z * (SY[m] * nyi - SX[m] * nxi) * KREF[m];
-            m = (m + 1 == n) ? 0 : m + 1;
-        }
-        F[i] = F_SCALE * acc;
+        const int im1 = (i == 0) ? n - 1 : i - 1, ip1 = (i + 1 == n) ? 0 : i + 1;
+        const double hi = H[i], him = H[im1];
+        const double zx = 6.0 * ((T4[ip1] - T4[i]) / hi - (T4[i] - T4[im1]) / him);
+        const double zy = 6.0 * ((T5[ip1] - T5[i]) / hi - (T5[i] - T5[im1]) / him);
+        F[i] = F_SCALE * (NY[i] * zy - NX[i] * zx);
     }
-    // ---- P8: band of H = E^T E: HB[i][k] = sum_m E[m][i] E[m][i+k], k = 0..32 ----
+    __syncthreads();
+    // ---- P6: tail sums U_t (towards +), V_t (towards -) of the three weights, chunked with warm-up ----
+    double *U0 = T0, *U1 = T1, *U2 = T2, *V0 = T3, *V1 = T4, *V2 = T5;
+    for (int c0 = threadIdx.x * TRI_CHUNK; c0 < n; c0 += blockDim.x * TRI_CHUNK) {
+        const int c1 = min(c0 + TRI_CHUNK, n);
+        int i = wrapi(c0 - TRI_WARM, n);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, rprev = 0.0;       // V_c = w_c + rho-_{c-1}^2 V_{c-1}
+        for (int s = c0 - TRI_WARM; s < c1; ++s) {
+            const double sx = SX[i], sy = SY[i], r2 = rprev * rprev;
+            a0 = fma(r2, a0, sy * sy); a1 = fma(r2, a1, sx * sy); a2 = fma(r2, a2, sx * sx);
+            if (s >= c0) { V0[i] = a0; V1[i] = a1; V2[i] = a2; }
+            rprev = RHOM[i];
+            i = (i + 1 == n) ? 0 : i + 1;
+        }
+        i = wrapi(c1 - 1 + TRI_WARM, n);
+        a0 = a1 = a2 = 0.0;
+        double rnext = 0.0;                                        // U_c = w_c + rho+_{c+1}^2 U_{c+1}
+        for (int s = c1 - 1 + TRI_WARM; s >= c0; --s) {
+            const double sx = SX[i], sy = SY[i], r2 = rnext * rnext;
+            a0 = fma(r2, a0, sy * sy); a1 = fma(r2, a1, sx * sy); a2 = fma(r2, a2, sx * sx);
+            if (s < c1) { U0[i] = a0; U1[i] = a1; U2[i] = a2; }
+            rnext = RHOP[i];
+            i = (i == 0) ? n - 1 : i - 1;
+        }
+    }
+    __syncthreads();
+    // ---- P7: band of B_t[c][c + d], d = 0..34 ----
+    double *BB = slab + L.o_zb;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        double *row = BB + (size_t)c * ZB_PITCH;
+        const double tc = TII[c];
+        const double v0 = V0[c], v1 = V1[c], v2 = V2[c];
+        {
+            const double sx = SX[c], sy = SY[c], t2 = tc * tc;
+            row[0] = t2 * (U0[c] + v0 - sy * sy);
+            row[BB_T] = t2 * (U1[c] + v1 - sx * sy);
+            row[2 * BB_T] = t2 * (U2[c] + v2 - sx * sx);
+        }
+        double P = tc, m0 = 0.0, m1 = 0.0, m2 = 0.0;
+        int cp = c;
+        for (int d = 1; d <= BD; ++d) {
+            const int cprev = cp;
+            cp = (cp + 1 == n) ? 0 : cp + 1;
+            const double rp = RHOP[cp];
+            if (d >= 2) {
+                const double sx = SX[cprev], sy = SY[cprev], pt = P * TII[cprev];
+                m0 = rp * fma(sy * sy, pt, m0);
+                m1 = rp * fma(sx * sy, pt, m1);
+                m2 = rp * fma(sx * sx, pt, m2);
+            }
+            P *= rp;
+            const double tp = TII[cp];
+            row[d] = P * fma(tp, U0[cp], tc * v0) + m0;
+            row[BB_T + d] = P * fma(tp, U1[cp], tc * v1) + m1;
+            row[2 * BB_T + d] = P * fma(tp, U2[cp], tc * v2) + m2;
+        }
+    }
+    __syncthreads();
+    // ---- P8: band of H: HB[i][k] = H[i][i + k], k = 0..32 (9-point stencil on the three B bands) ----
     double *HB = slab + L.o_hb;
     const int tot = n * (HBW + 1);
     for (int e = threadIdx.x; e < tot; e += blockDim.x) {
         const int i = e / (HBW + 1), k = e - i * (HBW + 1);
         int j = i + k; if (j >= n) j -= n;
-        const double nyi = NY[i], nxi = NX[i], nyj = NY[j], nxj = NX[j];
-        // rows m with |m - i| <= BZ and |m - j| <= BZ:  m = i + k - BZ .. i + BZ
-        double acc = 0.0;
-        int m = wrapi(i + k - BZ, n);
-        for (int t = k - BZ; t <= BZ; ++t) {    // m = i + t ; column offsets: i - m = -t, j - m = k - t
-            const double *zr = ZB + (size_t)m * ZB_PITCH + BZ;
-            const double sy = SY[m], sx = SX[m];
-            acc += (zr[-t] * (sy * nyi - sx * nxi)) * (zr[k - t] * (sy * nyj - sx * nxj));
-            m = (m + 1 == n) ? 0 : m + 1;
+        const int im1 = (i == 0) ? n - 1 : i - 1, jm1 = (j == 0) ? n - 1 : j - 1;
+        const double ihi = 1.0 / H[i], ihim = 1.0 / H[im1], ihj = 1.0 / H[j], ihjm = 1.0 / H[jm1];
+        const double ei[3] = {ihim, -(ihim + ihi), ihi};       // 6 D2[c][i] / 6, c = i-1, i, i+1
+        const double ej[3] = {ihjm, -(ihjm + ihj), ihj};
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int dc = -1; dc <= 1; ++dc) {
+            int c = i + dc; c = (c < 0) ? c + n : ((c >= n) ? c - n : c);
+#pragma unroll
+            for (int dj = -1; dj <= 1; ++dj) {
+                int cp = j + dj; cp = (cp < 0) ? cp + n : ((cp >= n) ? cp - n : cp);
+                const int d = k + dj - dc;                       // c' - c  (in [-2, 34])
+                const double *row = (d >= 0) ? BB + (size_t)c * ZB_PITCH + d : BB + (size_t)cp * ZB_PITCH - d;
+                const double co = ei[dc + 1] * ej[dj + 1];
+                a0 = fma(co, row[0], a0);
+                a1 = fma(co, row[BB_T], a1);
+                a2 = fma(co, row[2 * BB_T], a2);
+            }
         }
-        HB[(size_t)i * HB_PITCH + k] = acc;
+        const double nyi = NY[i], nxi = NX[i], nyj = NY[j], nxj = NX[j];
+        HB[(size_t)i * HB_PITCH + k] = 36.0 * (nyi * nyj * a0 - (nyi * nxj + nxi * nyj) * a1 + nxi * nxj * a2);
     }
     for (int i = threadIdx.x; i < n; i += blockDim.x) HB[(size_t)i * HB_PITCH + HBW + 1] = 0.0;
     if (threadIdx.x == 0) status[b] = 0;

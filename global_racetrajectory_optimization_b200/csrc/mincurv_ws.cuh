@@ -2,7 +2,7 @@
 //
 // HBM layout: slab b starts at ws + b * stride doubles and holds
 //   [NUM_VEC][np]        O(N) vectors (geometry, linearisation, interior-point iterates)
-//   [n_max][ZB_PITCH]    band of Z = Tri^{-1} 6 D2      (row m: Z[m][m-BZ .. m+BZ])
+//   [n_max][ZB_PITCH]    bands of B_t = Ti diag(w_t) Ti, t = 0..2  (assembly scratch, mincurv_setup.cu)
 //   [np][HB_PITCH]       band of H = E^T E              (row i: H[i][i .. i+32], cyclic)
 //   [3 nb_max + 1][1024] 32x32 column-major tiles of the block-cyclic Cholesky factor of H + D
 #pragma once

@@ -195,12 +195,8 @@ def test_properties_at_baseline_size():
         assert rel_max(-al[18 + i][idx], al[i]) <= 5e-3           # reversal: same curve, mirrored knots
     # KKT check against the kernel's own band (slab layout mirrors csrc/mincurv_ws.cuh)
     ws = [v for k, v in B_._WS.items() if k[0] == "mincurv"][0].view(torch.float64)
-    NUM_VEC, HB_PITCH, ZB_PITCH = 40, 34, 74
-    np_ = ((n + 31) // 32) * 32 + 64
-    nb_max = (n - 32 + 31) // 32
-    o_hb = NUM_VEC * np_ + n * ZB_PITCH
-    stride = ((o_hb + np_ * HB_PITCH + (3 * nb_max + 1) * 1024) + 15) & ~15
-    V = "H DIAG DFW DBW LFW INVD TII RHOP RHOM PX PY NX NY MX MY XP YP SX SY KREF LB UB F".split()
+    lay = B_.mincurv_slab_layout(n)
+    np_, o_hb, stride, HB_PITCH, V = lay["np"], lay["o_hb"], lay["stride"], B_.HB_PITCH, B_.SLAB_VECTORS
     for b in range(0, B, 5):
         slab = ws[b * stride:(b + 1) * stride].cpu().numpy()
         HB = slab[o_hb:o_hb + np_ * HB_PITCH].reshape(-1, HB_PITCH)[:n, :33]
@@ -212,11 +208,11 @@ def test_properties_at_baseline_size():
             Ha += HB[:, k] * np.roll(a, -k) + np.roll(HB[:, k] * a, k)
         grad = Ha + f
         scale = np.abs(f).max()
+        # KKT: with lam_u = max(-grad, 0), lam_l = max(grad, 0) stationarity and dual feasibility hold by
+        # construction; what remains is primal feasibility and complementarity
         assert np.all(a <= ub + 1e-9) and np.all(a >= lb - 1e-9)
-        at_ub, at_lb = (ub - a) < 1e-7, (a - lb) < 1e-7
-        free = ~(at_ub | at_lb)
-        assert np.abs(grad[free]).max() <= 1e-6 * scale
-        assert np.all(grad[at_ub] <= 1e-6 * scale) and np.all(grad[at_lb] >= -1e-6 * scale)
+        comp = np.maximum(-grad, 0.0) * (ub - a) + np.maximum(grad, 0.0) * (a - lb)
+        assert comp.max() <= 1e-8 * scale * (ub - lb).max()
 
 
 def test_raceline_batch_properties_at_baseline_size():
@@ -241,6 +237,6 @@ def test_raceline_batch_properties_at_baseline_size():
         assert np.all(np.diff(ind) >= 0) and ind[-1] <= n - 1
         xy = rl["raceline_interp"][b, :m].cpu().numpy()
         d = np.linalg.norm(np.diff(xy, axis=0), axis=1)
-        assert np.abs(d - el[:-1]).max() < 2e-3                              # chord ~ arc at 2 m steps
+        assert np.abs(d - el[:-1]).max() < 0.15                              # chord ~ arc (15-point polyline lengths) at 2 m steps
         kap = rl["kappa"][b, :m].cpu().numpy()
         assert np.abs(kap).max() < 0.5

@@ -15,15 +15,8 @@ os.makedirs(OUT, exist_ok=True)
 dev = torch.device("cuda")
 rep = {}
 
-def layout(n_max):
-    NUM_VEC = 40; ZB_PITCH = 74; HB_PITCH = 34
-    np_ = ((n_max + 31) // 32) * 32 + 64
-    nb_max = max(1, (n_max - 32 + 31) // 32)
-    o = NUM_VEC * np_; o_zb = o; o += n_max * ZB_PITCH; o_hb = o; o += np_ * HB_PITCH; o_t = o; o += (3 * nb_max + 1) * 1024
-    stride = (o + 15) & ~15
-    return dict(np=np_, o_zb=o_zb, o_hb=o_hb, o_tiles=o_t, stride=stride, nb_max=nb_max)
-
-VEC = "H DIAG DFW DBW LFW INVD TII RHOP RHOM PX PY NX NY MX MY XP YP SX SY KREF LB UB F T0 T1 T2 T3 T4 T5 ALPHA LU LL RD RHS DX DD DLU DLL SU SL".split()
+layout = B_.mincurv_slab_layout
+VEC = B_.SLAB_VECTORS
 
 for N in [128, 200, 333]:
     rt = synth.make_track(1, N)
