@@ -25,6 +25,7 @@ _SIGS = {
     "mc_mincurv_setup_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _c_dbl, _vp, _vp, _vp, _sz, _vp]),
     "mc_mincurv_pdip_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mc_mincurv_finalize_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _c_dbl, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mc_mincurv_kappa_batch": (_c_int, [_c_int, _c_int, _vp, _c_dbl, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mc_shortest_path_workspace_bytes": (_sz, [_c_int, _c_int]),
     "mc_shortest_path_solve_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _c_dbl, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mc_create_raceline_workspace_bytes": (_sz, [_c_int, _c_int]),
@@ -35,6 +36,7 @@ _SIGS = {
     "mc_iqp_relinearise_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_dbl, _c_int, _vp, _vp, _vp, _vp,
                                           _sz, _vp]),
     "mc_scale_alpha_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _c_dbl, _vp]),
+    "mc_debug_read_profile": (_c_int, [_vp, _c_int]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -24,7 +24,7 @@ STATUS_TEXT = {
     1: "Problem not solvable, track might be too small to run with current safety distance!",
     2: "interior-point iteration cap reached",
     3: "numerical breakdown (non-positive pivot)",
-    4: "curvature constraint rows are active at the box-constrained optimum",
+    4: "curvature rows still violated after the curvature-row phase (constraints inconsistent)",
     -1: "unsupported track size",
 }
 
@@ -32,7 +32,8 @@ _WS = {}
 
 # mirror of csrc/mincurv_ws.cuh (debugging / tests read intermediate results out of the workspace)
 SLAB_VECTORS = ("H DIAG DFW DBW LFW INVD TII RHOP RHOM PX PY NX NY MX MY XP YP SX SY KREF LB UB F "
-                "T0 T1 T2 T3 T4 T5 ALPHA LU LL RD RHS DX DD DLU DLL SU SL").split()
+                "T0 T1 T2 T3 T4 T5 ALPHA LU LL RD RHS DX DD DLU DLL SU SL ISU ISL YPAD "
+                "S3 S4 L3 L4 KL WK EDX T3K T4K VV").split()
 HB_PITCH = 34
 ZB_PITCH = 106
 
@@ -342,7 +343,7 @@ def iqp_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, ka
         alpha = res["alpha"]
         if it < iters_min:
             scale_alpha_batch(alpha, it * 1.0 / iters_min)
-        failed = (res["status"] != 0) & (res["status"] != 4)
+        failed = res["status"] != 0
         if fixed_iters is not None:
             done = active & (torch.full_like(active, it >= fixed_iters) | failed)
         else:

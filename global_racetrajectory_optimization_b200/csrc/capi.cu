@@ -9,10 +9,13 @@
 namespace mc {
 size_t spline_ws_doubles(int n_max);
 size_t pdip_smem_bytes();
+int debug_read_profile(unsigned long long *, int);
 void launch_mincurv_setup(int, int, const int32_t *, const double *, const double *, const double *, double,
                           const double *, double *, const Layout &, int32_t *, cudaStream_t);
 int launch_mincurv_pdip(int, int, const int32_t *, double *, const Layout &, const PdipParams &, double *, int32_t *,
                         int32_t *, int, cudaStream_t);
+int launch_mincurv_pdip_kappa(int, int, const int32_t *, double *, const Layout &, const PdipParams &, double, double *,
+                              int32_t *, int32_t *, int, cudaStream_t);
 void launch_mincurv_finalize(int, int, const int32_t *, double *, const Layout &, const double *, double, double *,
                              double *, int32_t *, cudaStream_t);
 void launch_calc_splines(int, int, const int32_t *, const double *, int, const double *, int, double *, double *,
@@ -48,6 +51,8 @@ static int bad(const char *msg) {
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 extern "C" {
+
+int mc_mincurv_kappa_batch(int, int, const int32_t *, double, double *, int32_t *, int32_t *, void *, size_t, void *);
 
 int mc_version(void) { return 100; }
 const char *mc_last_error(void) { return g_err; }
@@ -146,8 +151,38 @@ int mc_mincurv_solve_batch(int B, int n_max, const int32_t *n_pts, const double 
     if (rc) return rc;
     rc = mc_mincurv_pdip_batch(B, n_max, n_pts, alpha, status, iters, workspace, workspace_bytes, stream);
     if (rc) return rc;
-    return mc_mincurv_finalize_batch(B, n_max, n_pts, alpha, kappa_bound, curv_error_max, kappa_lin_max, status,
-                                     workspace, workspace_bytes, stream);
+    rc = mc_mincurv_finalize_batch(B, n_max, n_pts, alpha, kappa_bound, curv_error_max, kappa_lin_max, status, workspace,
+                                   workspace_bytes, stream);
+    if (rc) return rc;
+    // instances whose box-only optimum violates the curvature rows (status 4) are re-solved with the rows
+    rc = mc_mincurv_kappa_batch(B, n_max, n_pts, kappa_bound, alpha, status, iters, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    return mc_mincurv_finalize_batch(B, n_max, n_pts, alpha, kappa_bound, curv_error_max, kappa_lin_max, status, workspace,
+                                     workspace_bytes, stream);
+}
+
+int mc_mincurv_kappa_batch(int B, int n_max, const int32_t *n_pts, double kappa_bound, double *alpha, int32_t *status,
+                           int32_t *iters, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!alpha || !status) return bad("mc_mincurv_kappa_batch: NULL argument");
+    int rc = mincurv_args("mc_mincurv_kappa_batch", B, n_max, workspace, workspace_bytes);
+    if (rc) return rc;
+    mc::PdipParams prm;
+    prm.max_iter = 40;
+    prm.mu_rel = 1e-11;
+    prm.rd_rel = 1e-8;
+    prm.eta = 0.995;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int per_sm = (int)((227 * 1024) / mc::pdip_smem_bytes());
+    int grid = sms * (per_sm > 0 ? per_sm : 1);
+    if (grid > B) grid = B;
+    if (mc::launch_mincurv_pdip_kappa(B, n_max, n_pts, (double *)workspace, mc::make_layout(n_max), prm, kappa_bound, alpha,
+                                      status, iters, grid, (cudaStream_t)stream) != 0) {
+        snprintf(g_err, sizeof(g_err), "mincurv_pdip_kappa_kernel: cudaFuncSetAttribute failed");
+        return MC_ECUDA;
+    }
+    return check_cuda("mincurv_pdip_kappa_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -263,6 +298,12 @@ int mc_iqp_relinearise_batch(int B, int n_max, const int32_t *n_pts, const int32
     mc::launch_calc_splines(B, n_max_new, n_pts_new, reftrack_new, 4, nullptr, 0, nullptr, nullptr, normvec_new, nullptr,
                             spl, s);
     return check_cuda("calc_splines_kernel");
+}
+
+/* debug aid: cycle counters of CTA 0 of mincurv_pdip_kernel (16 x uint64): 0 A' assembly, 1 chol, 2 inverse,
+ * 3 barrier A, 4 phase B, 5 barrier B, 6 solves, 7 TMA waits (forward), 9 total, 10 factor, 11 QPs, 12 IPM iterations */
+int mc_debug_read_profile(unsigned long long *host_out16, int reset) {
+    return mc::debug_read_profile(host_out16, reset) == 0 ? MC_OK : MC_ECUDA;
 }
 
 int mc_scale_alpha_batch(int B, int n_max, double *alpha, const double *scale_batch, double scale, void *stream) {

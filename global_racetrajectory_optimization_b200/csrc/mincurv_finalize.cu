@@ -62,7 +62,7 @@ mincurv_finalize_kernel(int n_max, const int32_t *__restrict__ n_pts, double *__
     if (threadIdx.x == 0) {
         curv_error_max[b] = emax;
         if (kappa_lin_max) kappa_lin_max[b] = kmax;
-        if (st == 0 && kmax > kappa_bound * (1.0 + 1e-9)) status[b] = 4;
+        if (st == 0 && kmax > kappa_bound * (1.0 + 1e-7)) status[b] = 4;
     }
 }
 

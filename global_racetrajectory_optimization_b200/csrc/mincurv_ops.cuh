@@ -1,0 +1,148 @@
+// Block-cooperative device pieces shared by the assembly kernel (K2a) and the curvature-row phase of the
+// interior-point kernel (K2b'): the weighted band assembly  H_w = E^T diag(1 + w) E  in O(N b) and the O(N)
+// operator forms of E and E^T (see mincurv_setup.cu for the derivation).  All vectors live in the instance slab.
+#pragma once
+#include "mincurv_ws.cuh"
+
+namespace mc {
+
+constexpr int BD = 34;               // B_t band: offsets d = c' - c in [0, 34]
+constexpr int BB_T = BD + 1;         // 35 doubles per weight
+static_assert(3 * BB_T <= ZB_PITCH, "B band does not fit the slab pitch");
+
+
+// Band of H_w = E^T diag(1 + wk) E into the slab's HB (wk == nullptr: plain H = E^T E).
+// Uses V_T0..V_T5 and the B-band scratch; ends with the band written but NOT synchronised.
+__device__ inline void assemble_hband(double *slab, const Layout &L, int n, const double *__restrict__ wk) {
+    const double *H = vec(slab, L, V_H), *TII = vec(slab, L, V_TII), *RHOP = vec(slab, L, V_RHOP), *RHOM = vec(slab, L, V_RHOM);
+    const double *NX = vec(slab, L, V_NX), *NY = vec(slab, L, V_NY), *SX = vec(slab, L, V_SX), *SY = vec(slab, L, V_SY);
+    // ---- P6: tail sums U_t (towards +), V_t (towards -) of the three weights, chunked with warm-up ----
+    double *U0 = vec(slab, L, V_T0), *U1 = vec(slab, L, V_T1), *U2 = vec(slab, L, V_T2);
+    double *V0 = vec(slab, L, V_T3), *V1 = vec(slab, L, V_T4), *V2 = vec(slab, L, V_T5);
+    for (int c0 = threadIdx.x * TRI_CHUNK; c0 < n; c0 += blockDim.x * TRI_CHUNK) {
+        const int c1 = min(c0 + TRI_CHUNK, n);
+        int i = wrapi(c0 - TRI_WARM, n);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, rprev = 0.0;       // V_c = w_c + rho-_{c-1}^2 V_{c-1}
+        for (int s = c0 - TRI_WARM; s < c1; ++s) {
+            const double ww = wk ? 1.0 + wk[i] : 1.0;
+            const double sx = SX[i], sy = ww * SY[i], r2 = rprev * rprev;
+            a0 = fma(r2, a0, sy * SY[i]); a1 = fma(r2, a1, sx * sy); a2 = fma(r2, a2, ww * sx * sx);
+            if (s >= c0) { V0[i] = a0; V1[i] = a1; V2[i] = a2; }
+            rprev = RHOM[i];
+            i = (i + 1 == n) ? 0 : i + 1;
+        }
+        i = wrapi(c1 - 1 + TRI_WARM, n);
+        a0 = a1 = a2 = 0.0;
+        double rnext = 0.0;                                        // U_c = w_c + rho+_{c+1}^2 U_{c+1}
+        for (int s = c1 - 1 + TRI_WARM; s >= c0; --s) {
+            const double ww = wk ? 1.0 + wk[i] : 1.0;
+            const double sx = SX[i], sy = ww * SY[i], r2 = rnext * rnext;
+            a0 = fma(r2, a0, sy * SY[i]); a1 = fma(r2, a1, sx * sy); a2 = fma(r2, a2, ww * sx * sx);
+            if (s < c1) { U0[i] = a0; U1[i] = a1; U2[i] = a2; }
+            rnext = RHOP[i];
+            i = (i == 0) ? n - 1 : i - 1;
+        }
+    }
+    __syncthreads();
+    // ---- P7: band of B_t[c][c + d], d = 0..34 ----
+    double *BB = slab + L.o_zb;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        double *row = BB + (size_t)c * ZB_PITCH;
+        const double tc = TII[c];
+        const double v0 = V0[c], v1 = V1[c], v2 = V2[c];
+        {
+            const double ww = wk ? 1.0 + wk[c] : 1.0;
+            const double sx = SX[c], sy = SY[c], t2 = tc * tc;
+            row[0] = t2 * (U0[c] + v0 - ww * sy * sy);
+            row[BB_T] = t2 * (U1[c] + v1 - ww * sx * sy);
+            row[2 * BB_T] = t2 * (U2[c] + v2 - ww * sx * sx);
+        }
+        double P = tc, m0 = 0.0, m1 = 0.0, m2 = 0.0;
+        int cp = c;
+        for (int d = 1; d <= BD; ++d) {
+            const int cprev = cp;
+            cp = (cp + 1 == n) ? 0 : cp + 1;
+            const double rp = RHOP[cp];
+            if (d >= 2) {
+                const double ww = wk ? 1.0 + wk[cprev] : 1.0;
+                const double sx = SX[cprev], sy = SY[cprev], pt = ww * P * TII[cprev];
+                m0 = rp * fma(sy * sy, pt, m0);
+                m1 = rp * fma(sx * sy, pt, m1);
+                m2 = rp * fma(sx * sx, pt, m2);
+            }
+            P *= rp;
+            const double tp = TII[cp];
+            row[d] = P * fma(tp, U0[cp], tc * v0) + m0;
+            row[BB_T + d] = P * fma(tp, U1[cp], tc * v1) + m1;
+            row[2 * BB_T + d] = P * fma(tp, U2[cp], tc * v2) + m2;
+        }
+    }
+    __syncthreads();
+    // ---- P8: band of H: HB[i][k] = H[i][i + k], k = 0..32 (9-point stencil on the three B bands) ----
+    double *HB = slab + L.o_hb;
+    const int tot = n * (HBW + 1);
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+        const int i = e / (HBW + 1), k = e - i * (HBW + 1);
+        int j = i + k; if (j >= n) j -= n;
+        const int im1 = (i == 0) ? n - 1 : i - 1, jm1 = (j == 0) ? n - 1 : j - 1;
+        const double ihi = 1.0 / H[i], ihim = 1.0 / H[im1], ihj = 1.0 / H[j], ihjm = 1.0 / H[jm1];
+        const double ei[3] = {ihim, -(ihim + ihi), ihi};       // 6 D2[c][i] / 6, c = i-1, i, i+1
+        const double ej[3] = {ihjm, -(ihjm + ihj), ihj};
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int dc = -1; dc <= 1; ++dc) {
+            int c = i + dc; c = (c < 0) ? c + n : ((c >= n) ? c - n : c);
+#pragma unroll
+            for (int dj = -1; dj <= 1; ++dj) {
+                int cp = j + dj; cp = (cp < 0) ? cp + n : ((cp >= n) ? cp - n : cp);
+                const int d = k + dj - dc;                       // c' - c  (in [-2, 34])
+                const double *row = (d >= 0) ? BB + (size_t)c * ZB_PITCH + d : BB + (size_t)cp * ZB_PITCH - d;
+                const double co = ei[dc + 1] * ej[dj + 1];
+                a0 = fma(co, row[0], a0);
+                a1 = fma(co, row[BB_T], a1);
+                a2 = fma(co, row[2 * BB_T], a2);
+            }
+        }
+        const double nyi = NY[i], nxi = NX[i], nyj = NY[j], nxj = NX[j];
+        HB[(size_t)i * HB_PITCH + k] = 36.0 * (nyi * nyj * a0 - (nyi * nxj + nxi * nyj) * a1 + nxi * nxj * a2);
+    }
+}
+
+// out = E v = S_y Z (n_y v) - S_x Z (n_x v)   (r0, r1, y0, y1, z0, z1: scratch vectors; out may alias none of them)
+__device__ inline void apply_E(double *slab, const Layout &L, int n, const double *__restrict__ v, double *__restrict__ out,
+                               double *r0, double *r1, double *y0, double *y1, double *z0, double *z1) {
+    const double *H = vec(slab, L, V_H), *LFW = vec(slab, L, V_LFW), *INVD = vec(slab, L, V_INVD);
+    const double *NX = vec(slab, L, V_NX), *NY = vec(slab, L, V_NY), *SX = vec(slab, L, V_SX), *SY = vec(slab, L, V_SY);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int im1 = (i == 0) ? n - 1 : i - 1, ip1 = (i + 1 == n) ? 0 : i + 1;
+        const double hi = H[i], him = H[im1];
+        const double vx = NX[i] * v[i], vxm = NX[im1] * v[im1], vxp = NX[ip1] * v[ip1];
+        const double vy = NY[i] * v[i], vym = NY[im1] * v[im1], vyp = NY[ip1] * v[ip1];
+        r0[i] = 6.0 * ((vxp - vx) / hi - (vx - vxm) / him);
+        r1[i] = 6.0 * ((vyp - vy) / hi - (vy - vym) / him);
+    }
+    __syncthreads();
+    tri_solve2(LFW, INVD, H, r0, r1, y0, y1, z0, z1, n);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = SY[i] * z1[i] - SX[i] * z0[i];
+    __syncthreads();
+}
+
+// out = E^T v = N_y Z^T (S_y v) - N_x Z^T (S_x v),  Z^T = 6 D2 Tri^{-1}
+__device__ inline void apply_Et(double *slab, const Layout &L, int n, const double *__restrict__ v, double *__restrict__ out,
+                                double *r0, double *r1, double *y0, double *y1, double *z0, double *z1) {
+    const double *H = vec(slab, L, V_H), *LFW = vec(slab, L, V_LFW), *INVD = vec(slab, L, V_INVD);
+    const double *NX = vec(slab, L, V_NX), *NY = vec(slab, L, V_NY), *SX = vec(slab, L, V_SX), *SY = vec(slab, L, V_SY);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { r0[i] = SX[i] * v[i]; r1[i] = SY[i] * v[i]; }
+    __syncthreads();
+    tri_solve2(LFW, INVD, H, r0, r1, y0, y1, z0, z1, n);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int im1 = (i == 0) ? n - 1 : i - 1, ip1 = (i + 1 == n) ? 0 : i + 1;
+        const double hi = H[i], him = H[im1];
+        const double zx = 6.0 * ((z0[ip1] - z0[i]) / hi - (z0[i] - z0[im1]) / him);
+        const double zy = 6.0 * ((z1[ip1] - z1[i]) / hi - (z1[i] - z1[im1]) / him);
+        out[i] = NY[i] * zy - NX[i] * zx;
+    }
+    __syncthreads();
+}
+
+}  // namespace mc

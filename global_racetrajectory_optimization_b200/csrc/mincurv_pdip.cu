@@ -21,12 +21,12 @@
 // (F, S); warp 3 stages the band rows of the next block.  The factor goes to the instance's HBM slab as one
 // packed 32x33 tile per block (Linv_I lower | T_I upper) plus one 32x32 tile F_I; the triangular sweeps
 // are sequences of 32x32 mat-vecs over them.
-#include "mincurv_ws.cuh"
+#include "mincurv_ops.cuh"
 
 namespace mc {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int PD_THREADS = 128;
+constexpr int PD_THREADS = 96;
 constexpr int TP = 36;             // shared tile pitch (doubles): conflict-free DMMA fragment loads
 constexpr int LTP = 33;            // pitch of the packed (Linv | T) tile in HBM
 constexpr int LT_TILE = 32 * LTP;  // 1056 doubles
@@ -74,15 +74,19 @@ __device__ __forceinline__ double hentry(const double *HB, int n, int i, int j) 
     return 0.0;
 }
 
+// Phase cycle counters of CTA 0 / warp 0 (debug aid, read with mc_debug_read_profile): cheap enough to stay compiled in.
+__device__ unsigned long long g_prof[16];
+#define PROF_T0() const long long _pt0 = (blockIdx.x == 0 && (threadIdx.x & 31) == 0) ? clock64() : 0
+#define PROF_ADD(slot, t0) do { if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_prof[slot], (unsigned long long)(clock64() - (t0))); } while (0)
+
 struct PdShared {
-    double band[2][32 * HB_PITCH];   // band rows of the current / next chain block
-    // The five factorisation tiles; during the triangular sweeps the same 46 KB hold the two 16.5 KB
+    double band[32 * HB_PITCH];      // band rows of the current chain block (next block: prefetched in registers)
+    // The four factorisation tiles; during the triangular sweeps the same 36 KB hold the two 16.5 KB
     // staging buffers of the TMA tile pipeline (stage s at &As[0] + s * BLK_TILES).
     double As[32 * TP];              // A'_I -> L_II, column-major: As[c * TP + r]
     double Li[32 * TP];              // Linv_I, row-major
     double Ts[32 * TP];              // T_I, row-major (upper triangular)
-    double Fa[32 * TP];              // F tiles, ping
-    double Fb[32 * TP];              // pong
+    double Fa[32 * TP];              // F_{I-1} -> FW_I -> F_I, row-major (updated in place)
     uint64_t full_bar[2], empty_bar[2];
     double dinv[32];
     double vbuf[8][32];
@@ -90,221 +94,238 @@ struct PdShared {
     int flag;
 };
 
-// 32x32 Cholesky, lane = row, tile column-major in shared (As[c*TP + r]); in place, lower triangle only.
-// Left-looking over four 8-column panels: the contributions of the finished columns are subtracted with
-// eight independent accumulators (rolled loop, two broadcast LDS.128 + one LDS per step), then the 8-column
-// panel is factored in registers with warp shuffles.  Also writes dinv[r] = 1 / L[r][r].
-__device__ __forceinline__ bool chol32_smem(double *As, double *dinv, int lane) {
+// 1/sqrt(d) for a positive, normal d: hardware seed (rsqrt.approx.f64, ~2^-23) + one cubically convergent
+// correction y += y e (1/2 + 3/8 e), e = 1 - d y^2  (relative error ~2^-68 before rounding).  Six dependent
+// instructions instead of the library routine with its special-case slow path: the pivot chain of the
+// Cholesky is latency bound on exactly this.
+__device__ __forceinline__ double fast_rsqrt(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double t = d * y;
+    const double e = fma(-t, y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cholesky + explicit inverse of a 32x32 SPD block on 8x8 sub-blocks (one warp):
+//   A (lower triangle) column-major in As (As[c*TP + r]) -> L in As (lower), Linv = L^{-1} row-major in Li
+//   (full tile: zeros above the diagonal).
+// Panel J (columns 8J..8J+7):
+//   (1) A[:, J] -= sum_{K<J} L[:, K] L[J, K]^T               -- FP64 tensor cores (DMMA), 20 per block in total
+//   (2) the updated 8x8 diagonal block is broadcast to every lane (shuffles) and factored redundantly in
+//       registers, right-looking: the dependent chain per pivot is rsqrt + one multiply + one FMA; every lane
+//       applies the same eliminations to its own row (the panel solve comes for free);
+//   (3) the inverse of the diagonal block (8x8 triangular, registers, redundant) -> Li diagonal block.
+// Off-diagonal blocks of Linv, by block distance d = 1..3 (DMMA):  W = sum_{K=J}^{I-1} L_IK Linv_KJ,
+//   Linv_IJ = -Linv_II W   (W passes through its destination slot in Li to change fragment layout).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool chol_inv32(double *As, double *Li, int lane) {
+    const int g = lane >> 2, q = lane & 3;
     bool ok = true;
 #pragma unroll 1
     for (int J = 0; J < 4; ++J) {
         const int c0 = 8 * J;
+        const long long tp0 = clock64();
+        // ---- (1) panel update on the tensor cores ----
+        if (J > 0) {
+#pragma unroll 1
+            for (int I = J; I < 4; ++I) {
+                double c2[2];
+                c2[0] = As[(c0 + 2 * q) * TP + 8 * I + g];
+                c2[1] = As[(c0 + 2 * q + 1) * TP + 8 * I + g];
+#pragma unroll 1
+                for (int ks = 0; ks < 2 * J; ++ks)          // k = 4 ks + q runs over the finished columns 0 .. 8J-1
+                    dmma(c2, -As[(4 * ks + q) * TP + 8 * I + g], As[(4 * ks + q) * TP + c0 + g]);
+                As[(c0 + 2 * q) * TP + 8 * I + g] = c2[0];
+                As[(c0 + 2 * q + 1) * TP + 8 * I + g] = c2[1];
+            }
+            __syncwarp();
+        }
+        const long long tp1 = clock64();
+        // ---- (2) panel factorisation: lane = row ----
         double a[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) a[t] = As[(c0 + t) * TP + lane];
-#pragma unroll 2
-        for (int j = 0; j < c0; ++j) {
-            const double lr = -As[j * TP + lane];
-            const double2 b0 = *reinterpret_cast<const double2 *>(&As[j * TP + c0]);
-            const double2 b1 = *reinterpret_cast<const double2 *>(&As[j * TP + c0 + 2]);
-            const double2 b2 = *reinterpret_cast<const double2 *>(&As[j * TP + c0 + 4]);
-            const double2 b3 = *reinterpret_cast<const double2 *>(&As[j * TP + c0 + 6]);
-            a[0] = fma(lr, b0.x, a[0]); a[1] = fma(lr, b0.y, a[1]);
-            a[2] = fma(lr, b1.x, a[2]); a[3] = fma(lr, b1.y, a[3]);
-            a[4] = fma(lr, b2.x, a[4]); a[5] = fma(lr, b2.y, a[5]);
-            a[6] = fma(lr, b3.x, a[6]); a[7] = fma(lr, b3.y, a[7]);
-        }
+        double dg[8][8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+#pragma unroll
+            for (int w = 0; w <= v; ++w) dg[v][w] = __shfl_sync(FULL, a[w], c0 + v);
+        double rs[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            const double d = __shfl_sync(FULL, a[t], c0 + t);
-            if (!(d > 0.0)) ok = false;
-            const double rs = rsqrt(d);
-            const double l = a[t] * rs;
-            a[t] = l;
+            if (!(dg[t][t] > 0.0)) ok = false;
+            rs[t] = fast_rsqrt(dg[t][t]);
+            a[t] *= rs[t];
 #pragma unroll
-            for (int u = t + 1; u < 8; ++u) a[u] = fma(-l, __shfl_sync(FULL, l, c0 + u), a[u]);
-            if (lane == c0 + t) dinv[c0 + t] = rs;
+            for (int v = t + 1; v < 8; ++v) dg[v][t] *= rs[t];
+#pragma unroll
+            for (int v = t + 1; v < 8; ++v) {
+                a[v] = fma(-a[t], dg[v][t], a[v]);
+#pragma unroll
+                for (int w = t + 1; w <= v; ++w) dg[v][w] = fma(-dg[v][t], dg[w][t], dg[v][w]);
+            }
         }
 #pragma unroll
         for (int t = 0; t < 8; ++t)
             if (lane >= c0 + t) As[(c0 + t) * TP + lane] = a[t];
+        const long long tp2 = clock64();
+        // ---- (3) inverse of the diagonal block: X[v][t], v >= t  (dg[v][t] = L[v][t] for v > t, rs[t] = 1/L[t][t]) ----
+        // computed redundantly in every lane; lane (g, q) then stores row g, columns 2q, 2q+1 of the 8x8 block
+        // (selected with branch-free selects: a lane-indexed switch would diverge 32 ways)
+        double e0 = 0.0, e1 = 0.0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            double x[8];
+            x[t] = rs[t];
+#pragma unroll
+            for (int v = t + 1; v < 8; ++v) {
+                double acc = 0.0;
+#pragma unroll
+                for (int u = t; u < v; ++u) acc = fma(dg[v][u], x[u], acc);
+                x[v] = -acc * rs[v];
+            }
+#pragma unroll
+            for (int v = t; v < 8; ++v) {
+                const bool mine = (g == v) && (q == (t >> 1));
+                if (t & 1) e1 = mine ? x[v] : e1;
+                else e0 = mine ? x[v] : e0;
+            }
+        }
+        *reinterpret_cast<double2 *>(&Li[(c0 + g) * TP + c0 + 2 * q]) = make_double2(e0, e1);
+        // zero the blocks of Li to the right of the diagonal block (rows c0..c0+7, columns c0+8..31)
+        for (int e = lane; e < 8 * (24 - c0); e += 32) {
+            const int rr = e / (24 - c0), cc = e - rr * (24 - c0);
+            Li[(c0 + rr) * TP + c0 + 8 + cc] = 0.0;
+        }
+        __syncwarp();
+        if (blockIdx.x == 0 && lane == 0) {
+            const long long tp3 = clock64();
+            atomicAdd(&g_prof[13], (unsigned long long)(tp1 - tp0));
+            atomicAdd(&g_prof[14], (unsigned long long)(tp2 - tp1));
+            atomicAdd(&g_prof[8], (unsigned long long)(tp3 - tp2));
+        }
+    }
+    const long long tq0 = clock64();
+    // ---- off-diagonal blocks of the inverse, by block distance ----
+#pragma unroll 1
+    for (int d = 1; d < 4; ++d) {
+#pragma unroll 1
+        for (int J = 0; J + d < 4; ++J) {
+            const int I = J + d;
+            double w2[2] = {0.0, 0.0};
+#pragma unroll 1
+            for (int ks = 2 * J; ks < 2 * I; ++ks)       // k = 4 ks + q over blocks K = J .. I-1
+                dmma(w2, As[(4 * ks + q) * TP + 8 * I + g], Li[(4 * ks + q) * TP + 8 * J + g]);
+            *reinterpret_cast<double2 *>(&Li[(8 * I + g) * TP + 8 * J + 2 * q]) = make_double2(w2[0], w2[1]);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int J = 0; J + d < 4; ++J) {
+            const int I = J + d;
+            const double b0 = Li[(8 * I + q) * TP + 8 * J + g], b1 = Li[(8 * I + 4 + q) * TP + 8 * J + g];
+            double x2[2] = {0.0, 0.0};
+            dmma(x2, -Li[(8 * I + g) * TP + 8 * I + q], b0);
+            dmma(x2, -Li[(8 * I + g) * TP + 8 * I + 4 + q], b1);
+            __syncwarp();
+            *reinterpret_cast<double2 *>(&Li[(8 * I + g) * TP + 8 * J + 2 * q]) = make_double2(x2[0], x2[1]);
+        }
         __syncwarp();
     }
+    if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_prof[2], (unsigned long long)(clock64() - tq0));
     return ok;
 }
 
-// Linv = L^{-1}: lane = column c; L column-major in As, Linv row-major in Li (full tile written, zeros above the
-// diagonal).  Four 8-row panels: contributions of the finished rows with eight independent accumulators, then
-// the 8x8 triangular solve of the panel.
-__device__ __forceinline__ void trinv32_smem(const double *As, const double *dinv, double *Li, int lane) {
+// S[own 16 rows][:] -= F[own rows][:] F^T  (rolled over the four 8-wide k blocks to keep the code small)
+__device__ __forceinline__ void s_update(double (&sacc)[2][4][2], const double *Ft, int ib, int g, int q) {
 #pragma unroll 1
-    for (int R = 0; R < 4; ++R) {
-        const int r0 = 8 * R;
-        double sacc[8];
+    for (int ks = 0; ks < 8; ++ks) {
+        double a[2], b[4];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) sacc[t] = (r0 + t == lane) ? 1.0 : 0.0;
-#pragma unroll 2
-        for (int k = 0; k < r0; ++k) {
-            const double x = -Li[k * TP + lane];
-            const double2 b0 = *reinterpret_cast<const double2 *>(&As[k * TP + r0]);
-            const double2 b1 = *reinterpret_cast<const double2 *>(&As[k * TP + r0 + 2]);
-            const double2 b2 = *reinterpret_cast<const double2 *>(&As[k * TP + r0 + 4]);
-            const double2 b3 = *reinterpret_cast<const double2 *>(&As[k * TP + r0 + 6]);
-            sacc[0] = fma(b0.x, x, sacc[0]); sacc[1] = fma(b0.y, x, sacc[1]);
-            sacc[2] = fma(b1.x, x, sacc[2]); sacc[3] = fma(b1.y, x, sacc[3]);
-            sacc[4] = fma(b2.x, x, sacc[4]); sacc[5] = fma(b2.y, x, sacc[5]);
-            sacc[6] = fma(b3.x, x, sacc[6]); sacc[7] = fma(b3.y, x, sacc[7]);
-        }
-        double xv[8];
+        for (int i = 0; i < 2; ++i) a[i] = -Ft[(8 * (ib + i) + g) * TP + 4 * ks + q];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            double acc = sacc[t];
-#pragma unroll
-            for (int u = 0; u < t; ++u) acc = fma(-As[(r0 + u) * TP + r0 + t], xv[u], acc);
-            xv[t] = acc * dinv[r0 + t];
-            Li[(r0 + t) * TP + lane] = xv[t];
-        }
-        __syncwarp();
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// factorisation of M = H + diag(DD); returns false on a non-positive pivot
-// ------------------------------------------------------------------------------------------------
-__device__ __noinline__ bool factor(PdShared &sh, const double *__restrict__ HB, const double *__restrict__ DD,
-                       double *__restrict__ tiles, int n, int nb) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane >> 2, q = lane & 3;
-    const int NA = n - 32;
-    bool ok = true;
-    double sacc[2][4][2];          // warps 1,2: their 16 rows of the separator Schur complement (C fragments)
-    double *Fcur = sh.Fa, *Fnxt = sh.Fb;
-
-    // separator diagonal block C + D_S: gathered into As by all threads, then picked up as C fragments
-#pragma unroll 1
-    for (int e = threadIdx.x; e < 1024; e += PD_THREADS) {
-        const int r = e >> 5, c = e & 31;
-        double v = hentry(HB, n, NA + r, NA + c);
-        if (r == c) v += DD[NA + r];
-        sh.As[c * TP + r] = v;
-    }
-    __syncthreads();
-    if (warp == 1 || warp == 2) {
-        const int ib = 2 * (warp - 1);
+        for (int j = 0; j < 4; ++j) b[j] = Ft[(8 * j + g) * TP + 4 * ks + q];
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) sacc[i][j][e] = sh.As[(8 * j + 2 * q + e) * TP + 8 * (ib + i) + g];
+            for (int j = 0; j < 4; ++j) dmma(sacc[i][j], a[i], b[j]);
     }
-    __syncthreads();
-    // stage the band rows of block 0
-    for (int e = threadIdx.x; e < 32 * HB_PITCH; e += PD_THREADS) sh.band[0][e] = HB[e];
-    __syncthreads();
+}
 
-    for (int I = 0; I < nb; ++I) {
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// ---- warp 0: the chain.  Rounds I = 0..nb-1 are the chain blocks, round nb the separator block. ----
+__device__ __noinline__ bool factor_chain(PdShared &sh, const double *__restrict__ DD, double *__restrict__ tiles, int n, int nb) {
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int NA = n - 32;
+    bool ok = true;
+    __syncthreads();                      // fill warps have picked up the separator block from As
+    for (int I = 0; I <= nb; ++I) {
         const int base = 32 * I;
-        const double *band = sh.band[I & 1];
         // =========================== phase A ===========================
-        if (warp == 0) {
-            // ---- A' = A_I + D_I - T_I T_I^T (lower 8x8 blocks), written column-major into As ----
+        const long long tA = clock64();
+        if (I < nb) {
+            // ---- T_I T_I^T on the tensor cores first (lower 8x8 blocks) ... ----
+            double m2[10][2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0, bi = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j <= i; ++j) {
-                    double c2[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int r = 8 * i + g, c = 8 * j + 2 * q + e;
-                        const int lo = (c < r) ? c : r, dist = (c < r) ? r - c : c - r;
-                        double v = band[lo * HB_PITCH + dist];
-                        const bool real = (base + r) < NA && (base + c) < NA;
-                        if (!real) v = (r == c) ? 1.0 : 0.0;
-                        else if (r == c) v += DD[base + r];
-                        c2[e] = v;
-                    }
+                for (int j = 0; j <= i; ++j, ++bi) {
+                    m2[bi][0] = 0.0; m2[bi][1] = 0.0;
                     if (I > 0) {
-                        double m2[2] = {0.0, 0.0};
 #pragma unroll
                         for (int K = i; K < 4; ++K)      // T upper triangular: blocks (i,K), (j,K) nonzero for K >= i >= j
 #pragma unroll
                             for (int s = 0; s < 2; ++s)
-                                dmma(m2, sh.Ts[(8 * i + g) * TP + 8 * K + 4 * s + q], sh.Ts[(8 * j + g) * TP + 8 * K + 4 * s + q]);
-                        c2[0] -= m2[0];
-                        c2[1] -= m2[1];
+                                dmma(m2[bi], sh.Ts[(8 * i + g) * TP + 8 * K + 4 * s + q], sh.Ts[(8 * j + g) * TP + 8 * K + 4 * s + q]);
                     }
-                    sh.As[(8 * j + 2 * q) * TP + 8 * i + g] = c2[0];
-                    sh.As[(8 * j + 2 * q + 1) * TP + 8 * i + g] = c2[1];
                 }
-            }
+#pragma unroll
+            for (int i = 0, bi = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j, ++bi) {
+                    sh.As[(8 * j + 2 * q) * TP + 8 * i + g] = -m2[bi][0];
+                    sh.As[(8 * j + 2 * q + 1) * TP + 8 * i + g] = -m2[bi][1];
+                }
+            if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_prof[15], (unsigned long long)(clock64() - tA));
+            // ---- ... then A' = A_I + D_I - T T^T once the band rows of this block are in shared memory ----
+            if (I > 0) named_bar_sync(2, PD_THREADS);
             __syncwarp();
-            ok = chol32_smem(sh.As, sh.dinv, lane) && ok;
-            trinv32_smem(sh.As, sh.dinv, sh.Li, lane);
-        } else if (warp == 3) {
-            if (I + 1 < nb) {      // stage the band rows of the next block
-                double *dst = sh.band[(I + 1) & 1];
-                const double *src = HB + (size_t)(base + 32) * HB_PITCH;
-                for (int e = lane; e < 32 * HB_PITCH; e += 32) dst[e] = src[e];
+            {   // lower triangle (lane = row r, columns c <= r): As[c][r] += band entry (+ D on the diagonal)
+                const int r = lane;
+                const bool rreal = (base + r) < NA;
+                const double dd = rreal ? DD[base + r] : 0.0;
+#pragma unroll 4
+                for (int c = 0; c < 32; ++c) {
+                    if (c <= r) {
+                        double v = rreal ? sh.band[c * HB_PITCH + (r - c)] : ((r == c) ? 1.0 : 0.0);   // c < r <= NA-1-base => column real
+                        if (c == r) v += dd;
+                        sh.As[c * TP + r] += v;
+                    }
+                }
             }
         } else {
-            const int ib = 2 * (warp - 1);
-            // ---- S -= F_{I-1} F_{I-1}^T (own 16 rows) ----
-            if (I > 0) {
-#pragma unroll
-                for (int K = 0; K < 4; ++K)
-#pragma unroll
-                    for (int s = 0; s < 2; ++s) {
-                        double a[2], b[4];
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) a[i] = -Fcur[(8 * (ib + i) + g) * TP + 8 * K + 4 * s + q];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) b[j] = Fcur[(8 * j + g) * TP + 8 * K + 4 * s + q];
-#pragma unroll
-                        for (int i = 0; i < 2; ++i)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) dmma(sacc[i][j], a[i], b[j]);
-                    }
-            }
-            // ---- FW = Y_I - F_{I-1} T_I^T (own rows) -> Fnxt ----
-            const bool hasY = (I == 0) || (base + 31 >= NA - 32);
-            if (hasY) {      // Y_I = M[S, block I] is nonzero only across the wrap (I = 0) and next to the separator
-#pragma unroll 1
-                for (int e = lane; e < 512; e += 32) {
-                    const int r = 16 * (warp - 1) + (e >> 5), c = e & 31;
-                    Fnxt[r * TP + c] = ((base + c) < NA) ? hentry(HB, n, NA + r, base + c) : 0.0;
-                }
-                __syncwarp();
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    double c2[2] = {0.0, 0.0};
-                    if (hasY) {
-                        const double2 y2 = *reinterpret_cast<const double2 *>(&Fnxt[(8 * (ib + i) + g) * TP + 8 * j + 2 * q]);
-                        c2[0] = y2.x;
-                        c2[1] = y2.y;
-                    }
-                    if (I > 0) {
-                        double m2[2] = {0.0, 0.0};
-#pragma unroll
-                        for (int K = j; K < 4; ++K)      // T[c][k] != 0 for k >= c
-#pragma unroll
-                            for (int s = 0; s < 2; ++s)
-                                dmma(m2, Fcur[(8 * (ib + i) + g) * TP + 8 * K + 4 * s + q], sh.Ts[(8 * j + g) * TP + 8 * K + 4 * s + q]);
-                        c2[0] -= m2[0];
-                        c2[1] -= m2[1];
-                    }
-                    __syncwarp();
-                    *reinterpret_cast<double2 *>(&Fnxt[(8 * (ib + i) + g) * TP + 8 * j + 2 * q]) = make_double2(c2[0], c2[1]);
-                }
+            named_bar_sync(3, PD_THREADS);      // the fill warps have put the separator Schur complement into As
+        }
+        __syncwarp();
+        const long long tB = clock64();
+        ok = chol_inv32(sh.As, sh.Li, lane) && ok;
+        const long long tC = clock64();
+        const long long tD = tC;
+        if (blockIdx.x == 0 && lane == 0) {
+            atomicAdd(&g_prof[0], (unsigned long long)(tB - tA));
+            atomicAdd(&g_prof[1], (unsigned long long)(tC - tB));
         }
         __syncthreads();
+        const long long tE = clock64();
+        PROF_ADD(3, tD);
         // =========================== phase B ===========================
-        if (warp == 0) {
-            // Linv_I -> packed HBM tile (lower part, row-major pitch 33)
+        {
+            // Linv_I -> packed HBM tile (lower part, row-major pitch 33); round nb: the separator's slot
             double *gt = tiles + (size_t)I * BLK_TILES;
+#pragma unroll 4
             for (int r = 0; r < 32; ++r)
                 if (lane <= r) gt[r * LTP + lane] = sh.Li[r * TP + lane];
             if (I + 1 < nb) {
@@ -322,9 +343,9 @@ __device__ __noinline__ bool factor(PdShared &sh, const double *__restrict__ HB,
                                 for (int s = 0; s < 2; ++s) {
                                     // B_I[r][k] = M[base+32+r][base+k] = band[k][32 + r - k] for r <= k
                                     const int r = 8 * i + g, k = 8 * K + 4 * s + q;
-                                    double a = 0.0;
-                                    if (r <= k && (base + 32 + r) < NA) a = band[k * HB_PITCH + 32 + r - k];
-                                    dmma(c2, a, sh.Li[(8 * j + g) * TP + k]);
+                                    double av = 0.0;
+                                    if (r <= k && (base + 32 + r) < NA) av = sh.band[k * HB_PITCH + 32 + r - k];
+                                    dmma(c2, av, sh.Li[(8 * j + g) * TP + k]);
                                 }
                         }
                         const int r = 8 * i + g, c = 8 * j + 2 * q;
@@ -333,14 +354,107 @@ __device__ __noinline__ bool factor(PdShared &sh, const double *__restrict__ HB,
                         if (c + 1 >= r) gn[r * LTP + c + 2] = c2[1];
                     }
             }
-        } else if (warp == 1 || warp == 2) {
-            const int ib = 2 * (warp - 1);
-            // ---- F_I = FW Linv_I^T (own rows; Linv lower triangular: K <= j), in place in Fnxt ----
+        }
+        const long long tS2 = clock64();
+        PROF_ADD(4, tE);
+        __syncthreads();
+        PROF_ADD(5, tS2);
+    }
+    return ok;
+}
+
+// ---- warps 1, 2: the two 16-row halves of the separator fill row (F, S) + band prefetch for warp 0 ----
+__device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict__ HB, double *__restrict__ tiles, int n, int nb) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int NA = n - 32;
+    const int ib = 2 * (warp - 1);
+    double sacc[2][4][2];          // own 16 rows of the separator Schur complement (C fragments)
+    double breg[17];               // half of the next block's band rows (1088 doubles = 2 x 32 x 17)
+    double *Ft = sh.Fa;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) sacc[i][j][e] = sh.As[(8 * j + 2 * q + e) * TP + 8 * (ib + i) + g];
+    __syncthreads();
+    for (int I = 0; I <= nb; ++I) {
+        const int base = 32 * I;
+        // =========================== phase A ===========================
+        if (I == nb) {
+            // last round: the pending S -= F_{nb-1} F_{nb-1}^T, then the separator is handed to warp 0 through As
+            s_update(sacc, Ft, ib, g, q);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    sh.As[(8 * j + 2 * q) * TP + 8 * (ib + i) + g] = sacc[i][j][0];
+                    sh.As[(8 * j + 2 * q + 1) * TP + 8 * (ib + i) + g] = sacc[i][j][1];
+                }
+            __syncwarp();
+            named_bar_arrive(3, PD_THREADS);
+        } else {
+            // hand the prefetched band rows of this block to warp 0, then prefetch the next block's
+            if (I > 0) {
+#pragma unroll
+                for (int t = 0; t < 17; ++t) sh.band[(warp - 1) * 544 + 32 * t + lane] = breg[t];
+                __syncwarp();
+                named_bar_arrive(2, PD_THREADS);
+            }
+            if (I + 1 < nb) {
+                const double *src = HB + (size_t)(base + 32) * HB_PITCH + (warp - 1) * 544;
+#pragma unroll
+                for (int t = 0; t < 17; ++t) breg[t] = src[32 * t + lane];
+            }
+            // ---- S -= F_{I-1} F_{I-1}^T (own 16 rows, reads the whole F tile) ----
+            if (I > 0) s_update(sacc, Ft, ib, g, q);
+            // ---- FW = Y_I - F_{I-1} T_I^T, in place in the F tile (own rows) ----
+            double a[2][8];
+            if (I > 0) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) a[i][ks] = Ft[(8 * (ib + i) + g) * TP + 4 * ks + q];
+            }
+            named_bar_sync(1, 64);       // both fill warps are done reading F_{I-1}
+            const bool hasY = (I == 0) || (base + 31 >= NA - 32);
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    double c2[2] = {0.0, 0.0};
+                    if (hasY) {      // Y_I = M[S, block I]: nonzero only across the wrap (I = 0) and next to the separator
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int r = 8 * (ib + i) + g, c = 8 * j + 2 * q + e;
+                            if ((base + c) < NA) c2[e] = hentry(HB, n, NA + r, base + c);
+                        }
+                    }
+                    if (I > 0) {
+                        double m2[2] = {0.0, 0.0};
+                        for (int K = j; K < 4; ++K) {      // T[c][k] != 0 for k >= c
+                            const double ak0 = (K == 0) ? a[i][0] : (K == 1) ? a[i][2] : (K == 2) ? a[i][4] : a[i][6];
+                            const double ak1 = (K == 0) ? a[i][1] : (K == 1) ? a[i][3] : (K == 2) ? a[i][5] : a[i][7];
+                            dmma(m2, ak0, sh.Ts[(8 * j + g) * TP + 8 * K + q]);
+                            dmma(m2, ak1, sh.Ts[(8 * j + g) * TP + 8 * K + 4 + q]);
+                        }
+                        c2[0] -= m2[0];
+                        c2[1] -= m2[1];
+                    }
+                    *reinterpret_cast<double2 *>(&Ft[(8 * (ib + i) + g) * TP + 8 * j + 2 * q]) = make_double2(c2[0], c2[1]);
+                }
+            }
+        }
+        __syncthreads();
+        // =========================== phase B ===========================
+        if (I < nb) {
+            // ---- F_I = FW Linv_I^T (own rows; Linv lower triangular: K <= j), in place ----
             double a[2][8];
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) a[i][ks] = Fnxt[(8 * (ib + i) + g) * TP + 4 * ks + q];
+                for (int ks = 0; ks < 8; ++ks) a[i][ks] = Ft[(8 * (ib + i) + g) * TP + 4 * ks + q];
             __syncwarp();
             double *gf = tiles + (size_t)I * BLK_TILES + LT_TILE;
 #pragma unroll
@@ -353,47 +467,34 @@ __device__ __noinline__ bool factor(PdShared &sh, const double *__restrict__ HB,
 #pragma unroll
                         for (int s = 0; s < 2; ++s) dmma(c2, a[i][2 * K + s], sh.Li[(8 * j + g) * TP + 8 * K + 4 * s + q]);
                     const int r = 8 * (ib + i) + g, c = 8 * j + 2 * q;
-                    *reinterpret_cast<double2 *>(&Fnxt[r * TP + c]) = make_double2(c2[0], c2[1]);
+                    *reinterpret_cast<double2 *>(&Ft[r * TP + c]) = make_double2(c2[0], c2[1]);
                     gf[r * LTP + c] = c2[0];
                     gf[r * LTP + c + 1] = c2[1];
                 }
         }
-        { double *t = Fcur; Fcur = Fnxt; Fnxt = t; }
         __syncthreads();
     }
-    // ---- separator: S -= F_{nb-1} F_{nb-1}^T, handed over through As; chol + inverse by warp 0 ----
-    if (warp == 1 || warp == 2) {
-        const int ib = 2 * (warp - 1);
-#pragma unroll
-        for (int K = 0; K < 4; ++K)
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                double a[2], b[4];
-#pragma unroll
-                for (int i = 0; i < 2; ++i) a[i] = -Fcur[(8 * (ib + i) + g) * TP + 8 * K + 4 * s + q];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = Fcur[(8 * j + g) * TP + 8 * K + 4 * s + q];
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma(sacc[i][j], a[i], b[j]);
-            }
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                sh.As[(8 * j + 2 * q) * TP + 8 * (ib + i) + g] = sacc[i][j][0];
-                sh.As[(8 * j + 2 * q + 1) * TP + 8 * (ib + i) + g] = sacc[i][j][1];
-            }
+}
+
+__device__ __noinline__ bool factor(PdShared &sh, const double *__restrict__ HB, const double *__restrict__ DD,
+                                    double *__restrict__ tiles, int n, int nb) {
+    const int warp = threadIdx.x >> 5;
+    const int NA = n - 32;
+    // separator diagonal block C + D_S: gathered into As by all threads, then picked up as C fragments by the fill warps
+#pragma unroll 1
+    for (int e = threadIdx.x; e < 1024; e += PD_THREADS) {
+        const int r = e >> 5, c = e & 31;
+        double v = hentry(HB, n, NA + r, NA + c);
+        if (r == c) v += DD[NA + r];
+        sh.As[c * TP + r] = v;
     }
+    // band rows of block 0
+    for (int e = threadIdx.x; e < 32 * HB_PITCH; e += PD_THREADS) sh.band[e] = HB[e];
     __syncthreads();
     if (warp == 0) {
-        ok = chol32_smem(sh.As, sh.dinv, lane) && ok;
-        trinv32_smem(sh.As, sh.dinv, sh.Li, lane);
-        double *gt = tiles + (size_t)nb * BLK_TILES;     // separator inverse: row-major pitch 33 (lower part)
-        for (int r = 0; r < 32; ++r)
-            if (lane <= r) gt[r * LTP + lane] = sh.Li[r * TP + lane];
-        if (!ok) sh.flag = 1;
+        if (!factor_chain(sh, DD, tiles, n, nb)) sh.flag = 1;
+    } else {
+        factor_fill(sh, HB, tiles, n, nb);
     }
     __syncthreads();
     return sh.flag == 0;
@@ -404,7 +505,7 @@ __device__ __noinline__ bool factor(PdShared &sh, const double *__restrict__ HB,
 __device__ __forceinline__ double sm_t_mv(const double *LT, const double *v, int lane) {     // sum_{c >= r} T[r][c] v[c]
     const double *row = LT + lane * LTP + 1;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 2
+#pragma unroll 4
     for (int c = 0; c < 32; c += 4) {
         s0 = fma((c + 0 >= lane) ? row[c + 0] : 0.0, v[c + 0], s0);
         s1 = fma((c + 1 >= lane) ? row[c + 1] : 0.0, v[c + 1], s1);
@@ -416,7 +517,7 @@ __device__ __forceinline__ double sm_t_mv(const double *LT, const double *v, int
 __device__ __forceinline__ double sm_linv_mv(const double *LT, const double *v, int lane) {  // sum_{c <= r} Linv[r][c] v[c]
     const double *row = LT + lane * LTP;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 2
+#pragma unroll 4
     for (int c = 0; c < 32; c += 4) {
         s0 = fma((c + 0 <= lane) ? row[c + 0] : 0.0, v[c + 0], s0);
         s1 = fma((c + 1 <= lane) ? row[c + 1] : 0.0, v[c + 1], s1);
@@ -427,7 +528,7 @@ __device__ __forceinline__ double sm_linv_mv(const double *LT, const double *v, 
 }
 __device__ __forceinline__ double sm_linv_mtv(const double *LT, const double *v, int lane) { // sum_{r >= c} Linv[r][c] v[r]
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 2
+#pragma unroll 4
     for (int r = 0; r < 32; r += 4) {
         s0 = fma((r + 0 >= lane) ? LT[(r + 0) * LTP + lane] : 0.0, v[r + 0], s0);
         s1 = fma((r + 1 >= lane) ? LT[(r + 1) * LTP + lane] : 0.0, v[r + 1], s1);
@@ -438,7 +539,7 @@ __device__ __forceinline__ double sm_linv_mtv(const double *LT, const double *v,
 }
 __device__ __forceinline__ double sm_t_mtv(const double *LT, const double *v, int lane) {    // sum_{r <= c} T[r][c] v[r]
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 2
+#pragma unroll 4
     for (int r = 0; r < 32; r += 4) {
         s0 = fma((r + 0 <= lane) ? LT[(r + 0) * LTP + lane + 1] : 0.0, v[r + 0], s0);
         s1 = fma((r + 1 <= lane) ? LT[(r + 1) * LTP + lane + 1] : 0.0, v[r + 1], s1);
@@ -450,7 +551,7 @@ __device__ __forceinline__ double sm_t_mtv(const double *LT, const double *v, in
 __device__ __forceinline__ double sm_f_mv(const double *F, const double *v, int lane) {      // sum_c F[r][c] v[c]
     const double *row = F + lane * LTP;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 2
+#pragma unroll 4
     for (int c = 0; c < 32; c += 4) {
         s0 = fma(row[c + 0], v[c + 0], s0);
         s1 = fma(row[c + 1], v[c + 1], s1);
@@ -461,7 +562,7 @@ __device__ __forceinline__ double sm_f_mv(const double *F, const double *v, int 
 }
 __device__ __forceinline__ double sm_f_mtv(const double *F, const double *v, int lane) {     // sum_r F[r][c] v[r]
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 2
+#pragma unroll 4
     for (int r = 0; r < 32; r += 4) {
         s0 = fma(F[(r + 0) * LTP + lane], v[r + 0], s0);
         s1 = fma(F[(r + 1) * LTP + lane], v[r + 1], s1);
@@ -486,7 +587,7 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
     const unsigned nfill = 2u * nb + 1u;
     fence_proxy_async();        // the staging area was last written through the generic proxy (factor tiles)
     __syncthreads();
-    if (warp == 3) {
+    if (warp == 1) {
         if (lane == 0) {
             for (unsigned i = 0; i < nfill; ++i) {
                 const unsigned f = fill + i, st = f & 1u, k = f >> 1;
@@ -508,7 +609,9 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
             const unsigned f = fill + I, st = f & 1u, k = f >> 1;
             const double gv = gnext;
             if (I + 1 < nb) { const int nd = 32 * (I + 1) + lane; gnext = (nd < NA) ? g[nd] : 0.0; }
+            const long long tw = clock64();
             mbar_wait(&sh.full_bar[st], k & 1u);
+            PROF_ADD(7, tw);
             const double *LT = stage0 + st * BLK_TILES, *Ft = LT + LT_TILE;
             double v = gv;
             if (I > 0) v -= sm_t_mv(LT, yb, lane);
@@ -587,7 +690,7 @@ __device__ void band_matvec(const double *__restrict__ HB, const double *__restr
     }
 }
 
-__global__ void __launch_bounds__(PD_THREADS, 3)
+__global__ void __launch_bounds__(PD_THREADS, 4)
 mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double *__restrict__ ws, Layout L,
                     PdipParams prm, double *__restrict__ alpha_out, int32_t *__restrict__ status,
                     int32_t *__restrict__ iters_out) {
@@ -610,14 +713,16 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             if (iters_out && threadIdx.x == 0) iters_out[b] = 0;
             continue;
         }
+        const long long tq0 = clock64();
         double *slab = ws + (size_t)b * L.stride;
         const double *HB = slab + L.o_hb;
         double *tiles = slab + L.o_tiles;
-        const double *LB = vec(slab, L, V_LB), *UB = vec(slab, L, V_UB), *F = vec(slab, L, V_F);
-        double *AL = vec(slab, L, V_ALPHA), *LU = vec(slab, L, V_LU), *LL = vec(slab, L, V_LL), *RD = vec(slab, L, V_RD);
-        double *RHS = vec(slab, L, V_RHS), *DX = vec(slab, L, V_DX), *DD = vec(slab, L, V_DD);
-        double *TU = vec(slab, L, V_DLU), *TL = vec(slab, L, V_DLL), *SU = vec(slab, L, V_SU), *SL = vec(slab, L, V_SL);
-        double *YP = vec(slab, L, V_T4), *G0 = vec(slab, L, V_T0);
+        const double *__restrict__ LB = vec(slab, L, V_LB), *__restrict__ UB = vec(slab, L, V_UB), *__restrict__ F = vec(slab, L, V_F);
+        double *__restrict__ AL = vec(slab, L, V_ALPHA), *__restrict__ LU = vec(slab, L, V_LU), *__restrict__ LL = vec(slab, L, V_LL), *__restrict__ RD = vec(slab, L, V_RD);
+        double *__restrict__ RHS = vec(slab, L, V_RHS), *__restrict__ DX = vec(slab, L, V_DX), *__restrict__ DD = vec(slab, L, V_DD);
+        double *__restrict__ TU = vec(slab, L, V_DLU), *__restrict__ TL = vec(slab, L, V_DLL), *__restrict__ SU = vec(slab, L, V_SU), *__restrict__ SL = vec(slab, L, V_SL);
+        double *__restrict__ ISU = vec(slab, L, V_ISU), *__restrict__ ISL = vec(slab, L, V_ISL);
+        double *YP = vec(slab, L, V_YPAD), *G0 = vec(slab, L, V_T0);
         const int nb = (n - 32 + 31) / 32;
         if (threadIdx.x == 0) sh.flag = 0;
 
@@ -627,6 +732,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
         band_matvec(HB, AL, G0, n);
         __syncthreads();
         double gmax = 0.0, fmaxv = 0.0;
+#pragma unroll 1
         for (int i = threadIdx.x; i < n; i += PD_THREADS) {
             const double gi = G0[i] + F[i];
             G0[i] = gi;
@@ -637,6 +743,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
         fmaxv = block_reduce<1>(fmaxv, sh.red);
         const double lam0 = 1e-2 * gmax + 1e-300;
         double musum = 0.0;
+#pragma unroll 1
         for (int i = threadIdx.x; i < n; i += PD_THREADS) {
             const double gi = G0[i];
             const double lu = fmax(-gi, 0.0) + lam0, ll = fmax(gi, 0.0) + lam0;
@@ -647,6 +754,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             // cancellation once s << eps |alpha| (late iterations), see DESIGN.md
             const double su = UB[i] - a, sl = a - LB[i];
             SU[i] = su; SL[i] = sl;
+            ISU[i] = 1.0 / su; ISL[i] = 1.0 / sl;
             musum += su * lu + sl * ll;
         }
         musum = block_reduce<0>(musum, sh.red);
@@ -656,69 +764,88 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
         int it = 0;
         int result = 2;   // max-iter unless we converge
 
+        // Vector phases: the reciprocals 1/s_u, 1/s_l are state (ISU, ISL), so one interior-point iteration
+        // costs four divisions per variable; step lengths come from max-ratios (no division per element).
         for (it = 0; it < prm.max_iter; ++it) {
             // ---- barrier diagonal and affine right-hand side ----
-            for (int i = threadIdx.x; i < n; i += PD_THREADS) {
-                const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i];
-                DD[i] = lu / su + ll / sl;
+#pragma unroll 2
+    #pragma unroll 1
+        for (int i = threadIdx.x; i < n; i += PD_THREADS) {
+                const double lu = LU[i], ll = LL[i];
+                DD[i] = lu * ISU[i] + ll * ISL[i];
                 RHS[i] = -RD[i] + lu - ll;
             }
             __syncthreads();
+            const long long tf0 = clock64();
             if (!factor(sh, HB, DD, tiles, n, nb)) { result = 3; break; }
+            PROF_ADD(10, tf0);
+            const long long ts0 = clock64();
             fill = solve(sh, tiles, RHS, DX, YP, n, nb, fill);
-            // ---- affine step lengths, centring parameter ----
-            double ap = 1.0, ad = 1.0;
-            for (int i = threadIdx.x; i < n; i += PD_THREADS) {
+            PROF_ADD(6, ts0);
+            // ---- affine direction: step lengths 1 / max-ratio; mu_aff as a polynomial in (ap, ad) ----
+            double rp = 0.0, rdl = 0.0, c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll 2
+    #pragma unroll 1
+        for (int i = threadIdx.x; i < n; i += PD_THREADS) {
                 const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i];
-                const double dlu = -lu + lu * dx / su, dll = -ll - ll * dx / sl;
-                if (dx > 0.0) ap = fmin(ap, su / dx);
-                if (dx < 0.0) ap = fmin(ap, -sl / dx);
-                if (dlu < 0.0) ad = fmin(ad, -lu / dlu);
-                if (dll < 0.0) ad = fmin(ad, -ll / dll);
+                const double p = dx * ISU[i], m = dx * ISL[i];
+                rp = fmax(rp, fmax(p, -m));                 // s_u - a dx >= 0, s_l + a dx >= 0
+                rdl = fmax(rdl, fmax(1.0 - p, 1.0 + m));    // dlu / lu = -1 + p, dll / ll = -1 - m
+                const double dlu = lu * (p - 1.0), dll = -ll * (1.0 + m);
+                c00 += su * lu + sl * ll;
+                c01 += su * dlu + sl * dll;                 // coefficient of ad
+                c10 += dx * (ll - lu);                      // coefficient of ap
+                c11 += dx * (dll - dlu);                    // coefficient of ap * ad
             }
-            ap = block_reduce<2>(ap, sh.red);
-            ad = block_reduce<2>(ad, sh.red);
-            double mua = 0.0;
-            for (int i = threadIdx.x; i < n; i += PD_THREADS) {
-                const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i];
-                const double dlu = -lu + lu * dx / su, dll = -ll - ll * dx / sl;
-                mua += (su - ap * dx) * (lu + ad * dlu) + (sl + ap * dx) * (ll + ad * dll);
-            }
-            mua = block_reduce<0>(mua, sh.red) / (2.0 * n);
+            rp = block_reduce<1>(rp, sh.red);
+            rdl = block_reduce<1>(rdl, sh.red);
+            double ap = (rp > 1.0) ? 1.0 / rp : 1.0, ad = (rdl > 1.0) ? 1.0 / rdl : 1.0;
+            c00 = block_reduce<0>(c00, sh.red); c01 = block_reduce<0>(c01, sh.red);
+            c10 = block_reduce<0>(c10, sh.red); c11 = block_reduce<0>(c11, sh.red);
+            const double mua = (c00 + ad * c01 + ap * c10 + ap * ad * c11) / (2.0 * n);
             double sigma = mua / mu;
             sigma = sigma * sigma * sigma;
             const double smu = sigma * mu;
             // ---- corrector right-hand side ----
-            for (int i = threadIdx.x; i < n; i += PD_THREADS) {
-                const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i];
-                const double dlu = -lu + lu * dx / su, dll = -ll - ll * dx / sl;
-                const double tu = smu - su * lu - (-dx) * dlu;
+#pragma unroll 2
+    #pragma unroll 1
+        for (int i = threadIdx.x; i < n; i += PD_THREADS) {
+                const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i], isu = ISU[i], isl = ISL[i];
+                const double dlu = lu * (dx * isu - 1.0), dll = -ll * (1.0 + dx * isl);
+                const double tu = smu - su * lu + dx * dlu;
                 const double tl = smu - sl * ll - dx * dll;
                 TU[i] = tu; TL[i] = tl;
-                RHS[i] = -RD[i] - tu / su + tl / sl;
+                RHS[i] = -RD[i] - tu * isu + tl * isl;
             }
             __syncthreads();
+            const long long ts1 = clock64();
             fill = solve(sh, tiles, RHS, DX, YP, n, nb, fill);
-            ap = 1e300; ad = 1e300;
-            for (int i = threadIdx.x; i < n; i += PD_THREADS) {
-                const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i];
-                const double dlu = (TU[i] + lu * dx) / su, dll = (TL[i] - ll * dx) / sl;
-                if (dx > 0.0) ap = fmin(ap, su / dx);
-                if (dx < 0.0) ap = fmin(ap, -sl / dx);
-                if (dlu < 0.0) ad = fmin(ad, -lu / dlu);
-                if (dll < 0.0) ad = fmin(ad, -ll / dll);
+            PROF_ADD(6, ts1);
+            rp = 0.0; rdl = 0.0;
+#pragma unroll 2
+    #pragma unroll 1
+        for (int i = threadIdx.x; i < n; i += PD_THREADS) {
+                const double lu = LU[i], ll = LL[i], dx = DX[i], isu = ISU[i], isl = ISL[i];
+                const double dlu = (TU[i] + lu * dx) * isu, dll = (TL[i] - ll * dx) * isl;
+                rp = fmax(rp, fmax(dx * isu, -dx * isl));
+                rdl = fmax(rdl, fmax(-dlu / lu, -dll / ll));
             }
-            ap = fmin(1.0, prm.eta * block_reduce<2>(ap, sh.red));
-            ad = fmin(1.0, prm.eta * block_reduce<2>(ad, sh.red));
+            rp = block_reduce<1>(rp, sh.red);
+            rdl = block_reduce<1>(rdl, sh.red);
+            ap = (prm.eta < rp) ? prm.eta / rp : 1.0;       // min(1, eta / max-ratio)
+            ad = (prm.eta < rdl) ? prm.eta / rdl : 1.0;
             double musum2 = 0.0, rdmax = 0.0;
-            for (int i = threadIdx.x; i < n; i += PD_THREADS) {
+#pragma unroll 2
+    #pragma unroll 1
+        for (int i = threadIdx.x; i < n; i += PD_THREADS) {
                 const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i];
-                const double dlu = (TU[i] + lu * dx) / su, dll = (TL[i] - ll * dx) / sl;
+                const double dlu = (TU[i] + lu * dx) * ISU[i], dll = (TL[i] - ll * dx) * ISL[i];
                 const double an = AL[i] + ap * dx, lun = lu + ad * dlu, lln = ll + ad * dll;
                 const double sun = su - ap * dx, sln = sl + ap * dx;
                 // H dx = rhs - D dx  (M dx = rhs)
                 const double rdn = RD[i] + ap * (RHS[i] - DD[i] * dx) + ad * (dlu - dll);
                 AL[i] = an; LU[i] = lun; LL[i] = lln; RD[i] = rdn; SU[i] = sun; SL[i] = sln;
+                ISU[i] = 1.0 / sun; ISL[i] = 1.0 / sln;
                 musum2 += sun * lun + sln * lln;
                 rdmax = fmax(rdmax, fabs(rdn));
             }
@@ -733,10 +860,21 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             status[b] = result;
             if (iters_out) iters_out[b] = it;
         }
+        PROF_ADD(9, tq0);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&g_prof[11], 1ull); atomicAdd(&g_prof[12], (unsigned long long)it); }
     }
 }
 
 size_t pdip_smem_bytes() { return sizeof(PdShared); }
+
+int debug_read_profile(unsigned long long *host_out, int reset) {
+    if (cudaMemcpyFromSymbol(host_out, g_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        if (cudaMemcpyToSymbol(g_prof, z, sizeof(z)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
 
 int launch_mincurv_pdip(int B, int n_max, const int32_t *n_pts, double *ws, const Layout &L, const PdipParams &prm,
                         double *alpha, int32_t *status, int32_t *iters, int grid, cudaStream_t stream) {
@@ -748,6 +886,211 @@ int launch_mincurv_pdip(int B, int n_max, const int32_t *n_pts, double *ws, cons
         attr_set = true;
     }
     mincurv_pdip_kernel<<<grid, PD_THREADS, sizeof(PdShared), stream>>>(B, n_max, n_pts, ws, L, prm, alpha, status, iters);
+    return 0;
+}
+
+// ================================================================================================
+// K2b' -- the full QP of tph.opt_min_curv including the curvature rows |k_ref + E a| <= kappa_bound, for the
+// instances whose box-only optimum violates them (status 4 after K2c).  Same Mehrotra iteration; the rows enter
+// with slacks s3, s4 (infeasible start allowed) and multipliers l3, l4:
+//   M = H + D_box + E^T W E = E^T (I + W) E + D_box,  W = l3/s3 + l4/s4      -> weighted band assembly per iteration
+//   rhs = -(f + lu - ll) - tu/su + tl/sl - E^T v,  v = (kl - k_ref) + l3 - l4 + (t3 + l3 rp3)/s3 - (t4 + l4 rp4)/s4
+// with kl = k_ref + E a carried incrementally and E, E^T applied in O(N) operator form (mincurv_ops.cuh).
+// ================================================================================================
+__global__ void __launch_bounds__(PD_THREADS, 4)
+mincurv_pdip_kappa_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double *__restrict__ ws, Layout L,
+                          PdipParams prm, double kb, double *__restrict__ alpha_out, int32_t *__restrict__ status,
+                          int32_t *__restrict__ iters_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PdShared &sh = *reinterpret_cast<PdShared *>(smem_raw);
+    if (threadIdx.x == 0) {
+        mbar_init(&sh.full_bar[0], 1); mbar_init(&sh.full_bar[1], 1);
+        mbar_init(&sh.empty_bar[0], 1); mbar_init(&sh.empty_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned fill = 0;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        if (status[b] != 4) continue;
+        const int n = n_pts ? n_pts[b] : n_max;
+        double *aout = alpha_out + (size_t)b * n_max;
+        double *slab = ws + (size_t)b * L.stride;
+        const double *HB = slab + L.o_hb;
+        double *tiles = slab + L.o_tiles;
+        const double *__restrict__ LB = vec(slab, L, V_LB), *__restrict__ UB = vec(slab, L, V_UB), *__restrict__ F = vec(slab, L, V_F);
+        const double *__restrict__ KR = vec(slab, L, V_KREF);
+        double *__restrict__ AL = vec(slab, L, V_ALPHA), *__restrict__ LU = vec(slab, L, V_LU), *__restrict__ LL = vec(slab, L, V_LL);
+        double *__restrict__ RHS = vec(slab, L, V_RHS), *__restrict__ DX = vec(slab, L, V_DX), *__restrict__ DD = vec(slab, L, V_DD);
+        double *__restrict__ TU = vec(slab, L, V_DLU), *__restrict__ TL = vec(slab, L, V_DLL), *__restrict__ SU = vec(slab, L, V_SU), *__restrict__ SL = vec(slab, L, V_SL);
+        double *__restrict__ ISU = vec(slab, L, V_ISU), *__restrict__ ISL = vec(slab, L, V_ISL), *YP = vec(slab, L, V_YPAD);
+        double *__restrict__ S3 = vec(slab, L, V_S3), *__restrict__ S4 = vec(slab, L, V_S4), *__restrict__ L3 = vec(slab, L, V_L3), *__restrict__ L4 = vec(slab, L, V_L4);
+        double *__restrict__ KL = vec(slab, L, V_KL), *__restrict__ WK = vec(slab, L, V_WK), *__restrict__ EDX = vec(slab, L, V_EDX);
+        double *__restrict__ T3 = vec(slab, L, V_T3K), *__restrict__ T4 = vec(slab, L, V_T4K), *__restrict__ VV = vec(slab, L, V_VV), *__restrict__ ETV = vec(slab, L, V_RD);
+        double *t0 = vec(slab, L, V_T0), *t1 = vec(slab, L, V_T1), *t2 = vec(slab, L, V_T2), *t3 = vec(slab, L, V_T3), *t4 = vec(slab, L, V_T4), *t5 = vec(slab, L, V_T5);
+        const int nb = (n - 32 + 31) / 32;
+        const double m4 = 4.0 * n;
+        if (threadIdx.x == 0) sh.flag = 0;
+
+        // ---- start: box centre; kl = k_ref + E a; gradient g = E^T (E a) + f ----
+        for (int i = threadIdx.x; i < n; i += PD_THREADS) AL[i] = 0.5 * (LB[i] + UB[i]);
+        __syncthreads();
+        apply_E(slab, L, n, AL, EDX, t0, t1, t2, t3, t4, t5);
+        apply_Et(slab, L, n, EDX, ETV, t0, t1, t2, t3, t4, t5);
+        double gmax = 0.0, fmaxv = 0.0;
+        for (int i = threadIdx.x; i < n; i += PD_THREADS) {
+            gmax = fmax(gmax, fabs(ETV[i] + F[i]));
+            fmaxv = fmax(fmaxv, fabs(F[i]));
+        }
+        gmax = block_reduce<1>(gmax, sh.red);
+        fmaxv = block_reduce<1>(fmaxv, sh.red);
+        const double lam0 = 1e-2 * gmax + 1e-300;
+        double musum = 0.0;
+        for (int i = threadIdx.x; i < n; i += PD_THREADS) {
+            const double gi = ETV[i] + F[i];
+            const double lu = fmax(-gi, 0.0) + lam0, ll = fmax(gi, 0.0) + lam0;
+            const double a = AL[i], su = UB[i] - a, sl = a - LB[i];
+            const double kl = KR[i] + EDX[i];
+            const double s3 = fmax(kb - kl, 1e-2 * kb), s4 = fmax(kb + kl, 1e-2 * kb);
+            LU[i] = lu; LL[i] = ll; SU[i] = su; SL[i] = sl; ISU[i] = 1.0 / su; ISL[i] = 1.0 / sl;
+            KL[i] = kl; S3[i] = s3; S4[i] = s4; L3[i] = lam0; L4[i] = lam0;
+            musum += su * lu + sl * ll + (s3 + s4) * lam0;
+        }
+        musum = block_reduce<0>(musum, sh.red);
+        const double mu0 = musum / m4;
+        const double rd_tol = prm.rd_rel * (fmaxv + gmax) + 1e-300;
+        double mu = mu0;
+        int it = 0, result = 2;
+        double rdmax = 1e300, rpmax = 1e300;
+        for (it = 0; it < prm.max_iter + 20; ++it) {
+            // ---- weights, barrier diagonal, affine right-hand side ----
+            for (int i = threadIdx.x; i < n; i += PD_THREADS) {
+                const double s3 = S3[i], s4 = S4[i], l3 = L3[i], l4 = L4[i], kl = KL[i];
+                const double rp3 = kl + s3 - kb, rp4 = -kl + s4 - kb;
+                WK[i] = l3 / s3 + l4 / s4;
+                DD[i] = LU[i] * ISU[i] + LL[i] * ISL[i];
+                VV[i] = (kl - KR[i]) + l3 * rp3 / s3 - l4 * rp4 / s4;       // affine: t3 = -s3 l3, t4 = -s4 l4
+            }
+            __syncthreads();
+            assemble_hband(slab, L, n, WK);
+            __syncthreads();
+            apply_Et(slab, L, n, VV, ETV, t0, t1, t2, t3, t4, t5);
+            for (int i = threadIdx.x; i < n; i += PD_THREADS) RHS[i] = -F[i] - ETV[i];
+            __syncthreads();
+            if (!factor(sh, HB, DD, tiles, n, nb)) {
+                // E^T W E with W = l/s -> 1e12 and beyond is no longer numerically SPD: accept a late iterate, else give up
+                result = (mu <= 1e-7 * mu0 && rdmax <= 1e3 * rd_tol && rpmax <= 1e-6 * kb) ? 0 : 3;
+                break;
+            }
+            fill = solve(sh, tiles, RHS, DX, YP, n, nb, fill);
+            apply_E(slab, L, n, DX, EDX, t0, t1, t2, t3, t4, t5);
+            // ---- affine step lengths and centring ----
+            double rp = 0.0, rdl = 0.0, c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+            for (int i = threadIdx.x; i < n; i += PD_THREADS) {
+                const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i];
+                const double s3 = S3[i], s4 = S4[i], l3 = L3[i], l4 = L4[i], kl = KL[i], ed = EDX[i];
+                const double p = dx * ISU[i], m = dx * ISL[i];
+                const double ds3 = -(kl + s3 - kb) - ed, ds4 = -(-kl + s4 - kb) + ed;
+                const double dlu = lu * (p - 1.0), dll = -ll * (1.0 + m);
+                const double dl3 = -l3 - l3 * ds3 / s3, dl4 = -l4 - l4 * ds4 / s4;
+                rp = fmax(rp, fmax(fmax(p, -m), fmax(-ds3 / s3, -ds4 / s4)));
+                rdl = fmax(rdl, fmax(fmax(1.0 - p, 1.0 + m), fmax(-dl3 / l3, -dl4 / l4)));
+                c00 += su * lu + sl * ll + s3 * l3 + s4 * l4;
+                c01 += su * dlu + sl * dll + s3 * dl3 + s4 * dl4;
+                c10 += dx * (ll - lu) + ds3 * l3 + ds4 * l4;
+                c11 += dx * (dll - dlu) + ds3 * dl3 + ds4 * dl4;
+            }
+            rp = block_reduce<1>(rp, sh.red);
+            rdl = block_reduce<1>(rdl, sh.red);
+            double ap = (rp > 1.0) ? 1.0 / rp : 1.0, ad = (rdl > 1.0) ? 1.0 / rdl : 1.0;
+            c00 = block_reduce<0>(c00, sh.red); c01 = block_reduce<0>(c01, sh.red);
+            c10 = block_reduce<0>(c10, sh.red); c11 = block_reduce<0>(c11, sh.red);
+            const double mua = (c00 + ad * c01 + ap * c10 + ap * ad * c11) / m4;
+            double sigma = mua / mu;
+            sigma = sigma * sigma * sigma;
+            const double smu = sigma * mu;
+            // ---- corrector right-hand side ----
+            for (int i = threadIdx.x; i < n; i += PD_THREADS) {
+                const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i], isu = ISU[i], isl = ISL[i];
+                const double s3 = S3[i], s4 = S4[i], l3 = L3[i], l4 = L4[i], kl = KL[i], ed = EDX[i];
+                const double rp3 = kl + s3 - kb, rp4 = -kl + s4 - kb;
+                const double ds3 = -rp3 - ed, ds4 = -rp4 + ed;
+                const double dlu = lu * (dx * isu - 1.0), dll = -ll * (1.0 + dx * isl);
+                const double dl3 = -l3 - l3 * ds3 / s3, dl4 = -l4 - l4 * ds4 / s4;
+                const double tu = smu - su * lu + dx * dlu, tl = smu - sl * ll - dx * dll;
+                const double q3 = smu - s3 * l3 - ds3 * dl3, q4 = smu - s4 * l4 - ds4 * dl4;
+                TU[i] = tu; TL[i] = tl; T3[i] = q3; T4[i] = q4;
+                VV[i] = (kl - KR[i]) + l3 - l4 + (q3 + l3 * rp3) / s3 - (q4 + l4 * rp4) / s4;
+                RHS[i] = -(F[i] + lu - ll) - tu * isu + tl * isl;
+            }
+            __syncthreads();
+            apply_Et(slab, L, n, VV, ETV, t0, t1, t2, t3, t4, t5);
+            for (int i = threadIdx.x; i < n; i += PD_THREADS) RHS[i] -= ETV[i];
+            __syncthreads();
+            fill = solve(sh, tiles, RHS, DX, YP, n, nb, fill);
+            apply_E(slab, L, n, DX, EDX, t0, t1, t2, t3, t4, t5);
+            rp = 0.0; rdl = 0.0;
+            for (int i = threadIdx.x; i < n; i += PD_THREADS) {
+                const double lu = LU[i], ll = LL[i], dx = DX[i], isu = ISU[i], isl = ISL[i];
+                const double s3 = S3[i], s4 = S4[i], l3 = L3[i], l4 = L4[i], kl = KL[i], ed = EDX[i];
+                const double ds3 = -(kl + s3 - kb) - ed, ds4 = -(-kl + s4 - kb) + ed;
+                const double dlu = (TU[i] + lu * dx) * isu, dll = (TL[i] - ll * dx) * isl;
+                const double dl3 = (T3[i] - l3 * ds3) / s3, dl4 = (T4[i] - l4 * ds4) / s4;
+                rp = fmax(rp, fmax(fmax(dx * isu, -dx * isl), fmax(-ds3 / s3, -ds4 / s4)));
+                rdl = fmax(rdl, fmax(fmax(-dlu / lu, -dll / ll), fmax(-dl3 / l3, -dl4 / l4)));
+            }
+            rp = block_reduce<1>(rp, sh.red);
+            rdl = block_reduce<1>(rdl, sh.red);
+            ap = (prm.eta < rp) ? prm.eta / rp : 1.0;
+            ad = (prm.eta < rdl) ? prm.eta / rdl : 1.0;
+            double musum2 = 0.0;
+            rpmax = 0.0;
+            for (int i = threadIdx.x; i < n; i += PD_THREADS) {
+                const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i];
+                const double s3 = S3[i], s4 = S4[i], l3 = L3[i], l4 = L4[i], kl = KL[i], ed = EDX[i];
+                const double ds3 = -(kl + s3 - kb) - ed, ds4 = -(-kl + s4 - kb) + ed;
+                const double dlu = (TU[i] + lu * dx) * ISU[i], dll = (TL[i] - ll * dx) * ISL[i];
+                const double dl3 = (T3[i] - l3 * ds3) / s3, dl4 = (T4[i] - l4 * ds4) / s4;
+                const double sun = su - ap * dx, sln = sl + ap * dx, s3n = s3 + ap * ds3, s4n = s4 + ap * ds4;
+                const double lun = lu + ad * dlu, lln = ll + ad * dll, l3n = l3 + ad * dl3, l4n = l4 + ad * dl4;
+                const double kln = kl + ap * ed;
+                AL[i] += ap * dx; SU[i] = sun; SL[i] = sln; ISU[i] = 1.0 / sun; ISL[i] = 1.0 / sln;
+                LU[i] = lun; LL[i] = lln; S3[i] = s3n; S4[i] = s4n; L3[i] = l3n; L4[i] = l4n; KL[i] = kln;
+                VV[i] = (kln - KR[i]) + l3n - l4n;
+                musum2 += sun * lun + sln * lln + s3n * l3n + s4n * l4n;
+                rpmax = fmax(rpmax, fmax(fabs(kln + s3n - kb), fabs(-kln + s4n - kb)));
+            }
+            mu = block_reduce<0>(musum2, sh.red) / m4;
+            rpmax = block_reduce<1>(rpmax, sh.red);
+            __syncthreads();
+            // dual residual r_d = E^T (kl - k_ref + l3 - l4) + f + lu - ll   (exact every iteration, O(N))
+            apply_Et(slab, L, n, VV, ETV, t0, t1, t2, t3, t4, t5);
+            rdmax = 0.0;
+            for (int i = threadIdx.x; i < n; i += PD_THREADS) rdmax = fmax(rdmax, fabs(ETV[i] + F[i] + LU[i] - LL[i]));
+            rdmax = block_reduce<1>(rdmax, sh.red);
+            if (mu <= prm.mu_rel * mu0 && rdmax <= rd_tol && rpmax <= 1e-8 * kb) { result = 0; ++it; break; }
+            if (mu <= 1e-2 * prm.mu_rel * mu0) { result = (rdmax <= 1e3 * rd_tol && rpmax <= 1e-6 * kb) ? 0 : 2; ++it; break; }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_max; i += PD_THREADS) aout[i] = (i < n) ? AL[i] : 0.0;
+        if (threadIdx.x == 0) {
+            status[b] = result;
+            if (iters_out) iters_out[b] += it;
+        }
+    }
+}
+
+int launch_mincurv_pdip_kappa(int B, int n_max, const int32_t *n_pts, double *ws, const Layout &L, const PdipParams &prm,
+                              double kappa_bound, double *alpha, int32_t *status, int32_t *iters, int grid, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(mincurv_pdip_kappa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(PdShared));
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    mincurv_pdip_kappa_kernel<<<grid, PD_THREADS, sizeof(PdShared), stream>>>(B, n_max, n_pts, ws, L, prm, kappa_bound, alpha,
+                                                                             status, iters);
     return 0;
 }
 

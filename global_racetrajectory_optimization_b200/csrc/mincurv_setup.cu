@@ -17,13 +17,9 @@
 //   Mid_t(c, c'+1) = rho+_{c'+1} (Mid_t(c, c') + w_t[c'] Ti[c'][c] Ti[c'][c'])
 // (exact sums over all m -- no truncation of E -- verified against the explicit E^T E in tools/).
 // One CTA per QP instance; O(N) vectors and the B / H bands live in the instance's HBM slab.
-#include "mincurv_ws.cuh"
+#include "mincurv_ops.cuh"
 
 namespace mc {
-
-constexpr int BD = 34;               // B_t band: offsets d = c' - c in [0, 34]
-constexpr int BB_T = BD + 1;         // 35 doubles per weight
-static_assert(3 * BB_T <= ZB_PITCH, "B band does not fit the slab pitch");
 
 __global__ void __launch_bounds__(256)
 mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
@@ -119,91 +115,8 @@ mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
         F[i] = F_SCALE * (NY[i] * zy - NX[i] * zx);
     }
     __syncthreads();
-    // ---- P6: tail sums U_t (towards +), V_t (towards -) of the three weights, chunked with warm-up ----
-    double *U0 = T0, *U1 = T1, *U2 = T2, *V0 = T3, *V1 = T4, *V2 = T5;
-    for (int c0 = threadIdx.x * TRI_CHUNK; c0 < n; c0 += blockDim.x * TRI_CHUNK) {
-        const int c1 = min(c0 + TRI_CHUNK, n);
-        int i = wrapi(c0 - TRI_WARM, n);
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, rprev = 0.0;       // V_c = w_c + rho-_{c-1}^2 V_{c-1}
-        for (int s = c0 - TRI_WARM; s < c1; ++s) {
-            const double sx = SX[i], sy = SY[i], r2 = rprev * rprev;
-            a0 = fma(r2, a0, sy * sy); a1 = fma(r2, a1, sx * sy); a2 = fma(r2, a2, sx * sx);
-            if (s >= c0) { V0[i] = a0; V1[i] = a1; V2[i] = a2; }
-            rprev = RHOM[i];
-            i = (i + 1 == n) ? 0 : i + 1;
-        }
-        i = wrapi(c1 - 1 + TRI_WARM, n);
-        a0 = a1 = a2 = 0.0;
-        double rnext = 0.0;                                        // U_c = w_c + rho+_{c+1}^2 U_{c+1}
-        for (int s = c1 - 1 + TRI_WARM; s >= c0; --s) {
-            const double sx = SX[i], sy = SY[i], r2 = rnext * rnext;
-            a0 = fma(r2, a0, sy * sy); a1 = fma(r2, a1, sx * sy); a2 = fma(r2, a2, sx * sx);
-            if (s < c1) { U0[i] = a0; U1[i] = a1; U2[i] = a2; }
-            rnext = RHOP[i];
-            i = (i == 0) ? n - 1 : i - 1;
-        }
-    }
-    __syncthreads();
-    // ---- P7: band of B_t[c][c + d], d = 0..34 ----
-    double *BB = slab + L.o_zb;
-    for (int c = threadIdx.x; c < n; c += blockDim.x) {
-        double *row = BB + (size_t)c * ZB_PITCH;
-        const double tc = TII[c];
-        const double v0 = V0[c], v1 = V1[c], v2 = V2[c];
-        {
-            const double sx = SX[c], sy = SY[c], t2 = tc * tc;
-            row[0] = t2 * (U0[c] + v0 - sy * sy);
-            row[BB_T] = t2 * (U1[c] + v1 - sx * sy);
-            row[2 * BB_T] = t2 * (U2[c] + v2 - sx * sx);
-        }
-        double P = tc, m0 = 0.0, m1 = 0.0, m2 = 0.0;
-        int cp = c;
-        for (int d = 1; d <= BD; ++d) {
-            const int cprev = cp;
-            cp = (cp + 1 == n) ? 0 : cp + 1;
-            const double rp = RHOP[cp];
-            if (d >= 2) {
-                const double sx = SX[cprev], sy = SY[cprev], pt = P * TII[cprev];
-                m0 = rp * fma(sy * sy, pt, m0);
-                m1 = rp * fma(sx * sy, pt, m1);
-                m2 = rp * fma(sx * sx, pt, m2);
-            }
-            P *= rp;
-            const double tp = TII[cp];
-            row[d] = P * fma(tp, U0[cp], tc * v0) + m0;
-            row[BB_T + d] = P * fma(tp, U1[cp], tc * v1) + m1;
-            row[2 * BB_T + d] = P * fma(tp, U2[cp], tc * v2) + m2;
-        }
-    }
-    __syncthreads();
-    // ---- P8: band of H: HB[i][k] = H[i][i + k], k = 0..32 (9-point stencil on the three B bands) ----
+    assemble_hband(slab, L, n, nullptr);
     double *HB = slab + L.o_hb;
-    const int tot = n * (HBW + 1);
-    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
-        const int i = e / (HBW + 1), k = e - i * (HBW + 1);
-        int j = i + k; if (j >= n) j -= n;
-        const int im1 = (i == 0) ? n - 1 : i - 1, jm1 = (j == 0) ? n - 1 : j - 1;
-        const double ihi = 1.0 / H[i], ihim = 1.0 / H[im1], ihj = 1.0 / H[j], ihjm = 1.0 / H[jm1];
-        const double ei[3] = {ihim, -(ihim + ihi), ihi};       // 6 D2[c][i] / 6, c = i-1, i, i+1
-        const double ej[3] = {ihjm, -(ihjm + ihj), ihj};
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-#pragma unroll
-        for (int dc = -1; dc <= 1; ++dc) {
-            int c = i + dc; c = (c < 0) ? c + n : ((c >= n) ? c - n : c);
-#pragma unroll
-            for (int dj = -1; dj <= 1; ++dj) {
-                int cp = j + dj; cp = (cp < 0) ? cp + n : ((cp >= n) ? cp - n : cp);
-                const int d = k + dj - dc;                       // c' - c  (in [-2, 34])
-                const double *row = (d >= 0) ? BB + (size_t)c * ZB_PITCH + d : BB + (size_t)cp * ZB_PITCH - d;
-                const double co = ei[dc + 1] * ej[dj + 1];
-                a0 = fma(co, row[0], a0);
-                a1 = fma(co, row[BB_T], a1);
-                a2 = fma(co, row[2 * BB_T], a2);
-            }
-        }
-        const double nyi = NY[i], nxi = NX[i], nyj = NY[j], nxj = NX[j];
-        HB[(size_t)i * HB_PITCH + k] = 36.0 * (nyi * nyj * a0 - (nyi * nxj + nxi * nyj) * a1 + nxi * nxj * a2);
-    }
     for (int i = threadIdx.x; i < n; i += blockDim.x) HB[(size_t)i * HB_PITCH + HBW + 1] = 0.0;
     if (threadIdx.x == 0) status[b] = 0;
 }

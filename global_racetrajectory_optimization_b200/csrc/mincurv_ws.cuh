@@ -16,6 +16,8 @@ enum Vec : int {
     V_LB, V_UB, V_F,
     V_T0, V_T1, V_T2, V_T3, V_T4, V_T5,
     V_ALPHA, V_LU, V_LL, V_RD, V_RHS, V_DX, V_DD, V_DLU, V_DLL, V_SU, V_SL,
+    V_ISU, V_ISL, V_YPAD,                                   // reciprocal slacks, padded forward-solve vector
+    V_S3, V_S4, V_L3, V_L4, V_KL, V_WK, V_EDX, V_T3K, V_T4K, V_VV,   // curvature-row phase (K2b')
     NUM_VEC
 };
 

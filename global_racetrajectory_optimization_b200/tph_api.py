@@ -29,8 +29,10 @@ def _up(a, dtype=torch.float64):
 
 
 def _raise_status(st: int):
-    if st == 0 or st == 4:
+    if st == 0:
         return
+    if st == 4:     # still violated after the curvature-row phase: the rows cannot be met inside the track
+        raise ValueError("constraints are inconsistent, no solution")
     if st == 1:
         raise RuntimeError(_b.STATUS_TEXT[1])
     if st == 3:
@@ -73,12 +75,7 @@ def opt_min_curv(reftrack: np.ndarray, normvectors: np.ndarray, A, kappa_bound: 
         raise NotImplementedError("open tracks (closed=False) are outside the B200 hot path")
     h = h_from_system(A, no_points)
     res = _b.opt_min_curv_batch(_up(reftrack), _up(normvectors), _up(h), kappa_bound, float(w_veh))
-    st = int(res["status"][0].item())
-    _raise_status(st)
-    if st == 4:
-        raise NotImplementedError("the curvature constraint |kappa| <= kappa_bound is active for this track: "
-                                  "the curvature-row phase of the solver is not implemented yet "
-                                  f"(max linearised |kappa| = {float(res['kappa_lin_max'][0]):.4f})")
+    _raise_status(int(res["status"][0].item()))
     alpha = res["alpha"][0].cpu().numpy()
     if print_debug:
         print("IPM iterations opt_min_curv: %i" % int(res["iters"][0].item()))

@@ -17,8 +17,8 @@
  *   - per-instance results are reported in status[b] (int32):
  *       0 ok | 1 track too narrow ("Problem not solvable, track might be too small ...", tph RuntimeError)
  *       2 iteration cap reached | 3 numerical breakdown (non-positive pivot)
- *       4 curvature rows |k_ref + E alpha| <= kappa_bound active/violated at the box-only optimum
- *         (the result is then the optimum of the box-constrained QP only).
+ *       4 (transient) curvature rows |k_ref + E alpha| <= kappa_bound violated by the box-only optimum: set by the
+ *         finalize stage, consumed by mc_mincurv_kappa_batch, which re-solves the instance with the rows.
  */
 #ifndef MINCURV_B200_H
 #define MINCURV_B200_H
@@ -99,6 +99,11 @@ int mc_mincurv_pdip_batch(int B, int n_max, const int32_t *n_pts, double *alpha,
 int mc_mincurv_finalize_batch(int B, int n_max, const int32_t *n_pts, const double *alpha, double kappa_bound,
                               double *curv_error_max, double *kappa_lin_max, int32_t *status,
                               void *workspace, size_t workspace_bytes, void *stream);
+/* Fourth stage, run by mc_mincurv_solve_batch between two finalize passes: re-solves every instance flagged
+ * status 4 (curvature rows violated by the box-only optimum) as the full QP tph hands to quadprog, rows
+ * |k_ref + E alpha| <= kappa_bound included; leaves all other instances untouched. */
+int mc_mincurv_kappa_batch(int B, int n_max, const int32_t *n_pts, double kappa_bound, double *alpha, int32_t *status,
+                           int32_t *iters, void *workspace, size_t workspace_bytes, void *stream);
 
 /* -------------------------------------------------------------------------------------------------
  * tph.opt_shortest_path.opt_shortest_path(reftrack, normvectors, w_veh, print_debug)
@@ -158,6 +163,10 @@ int mc_iqp_relinearise_batch(int B, int n_max, const int32_t *n_pts, const int32
 /* alpha[b][:] *= scale_batch[b] (or the scalar `scale` when scale_batch is NULL): the damping
  * `alpha *= iter / iters_min` of tph.iqp_handler. */
 int mc_scale_alpha_batch(int B, int n_max, double *alpha, const double *scale_batch, double scale, void *stream);
+
+/* Debug aid (synchronous): reads (and optionally clears) 16 cycle counters that CTA 0 of mincurv_pdip_kernel
+ * accumulates per phase -- used by tools/prof_run.py to attribute time inside the kernel. Host pointer. */
+int mc_debug_read_profile(unsigned long long *host_out16, int reset);
 
 #ifdef __cplusplus
 }

@@ -149,6 +149,9 @@ CASES = {
     "synth500": (lambda: synth.make_track(14, 500), 2.0, 0.12, False),
     "synth500_narrow": (lambda: synth.make_track(15, 500), 5.2, 0.12, False),
     "synth1000": (lambda: synth.make_track(16, 1000), 2.0, 0.12, False),
+    # curvature rows |k_ref + E alpha| <= kappa_bound active at the optimum (tight kappa_bound)
+    "synth160_kappa": (lambda: synth.make_track(3, 160), 2.0, 0.02, False),
+    "synth333_kappa": (lambda: synth.make_track(13, 333), 2.0, 0.03, False),
 }
 
 

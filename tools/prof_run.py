@@ -17,3 +17,15 @@ for r in range(reps):
     torch.cuda.synchronize(); dt = time.time() - t0
 st = res["status"].cpu().numpy(); it = res["iters"].cpu().numpy()
 print("prof_run", Bn, N, f"{dt*1e3:.2f} ms {Bn/dt:.0f} QP/s status", np.bincount(st[st >= 0], minlength=5).tolist(), "iters", it.min(), float(it.mean()), it.max())
+
+import ctypes
+from global_racetrajectory_optimization_b200 import _lib
+buf = (ctypes.c_ulonglong * 16)()
+_lib.load().mc_debug_read_profile(ctypes.cast(buf, ctypes.c_void_p), 1)
+names = ["Aasm", "chol_inv", "ci_offdiag", "barA", "phaseB", "barB", "solves", "tma_wait", "ci_locinv", "total", "factor", "nqp", "iters", "ci_dmma_upd", "ci_panel", "Aasm_dmma"]
+vals = list(buf)
+nq = max(vals[11], 1)
+print("profile (cycles per QP of CTA 0, %d QPs, %.1f iters/QP):" % (vals[11], vals[12] / nq))
+for k, nm in enumerate(names):
+    if nm != "-" and (k < 11 or k > 12):
+        print("  %-9s %12.0f  %5.1f%%" % (nm, vals[k] / nq, 100.0 * vals[k] / max(vals[9], 1)))
