@@ -28,7 +28,7 @@ if ROOT not in sys.path:
 METRIC = "min-curv QPs/sec (N=1000 closed track, batched)"
 UNIT = "QP/s"
 N_POINTS = 1000
-BATCH_PER_GPU = 1024
+BATCH_PER_GPU = 2368          # 4 instances per resident CTA (148 SMs x 4 CTAs)
 N_BASE_LINES = 32          # distinct centre lines per rank; the rest of the batch are width-jitter variants
 KAPPA_BOUND = 0.12
 W_VEH = 2.0

@@ -13,9 +13,9 @@ int debug_read_profile(unsigned long long *, int);
 void launch_mincurv_setup(int, int, const int32_t *, const double *, const double *, const double *, double,
                           const double *, double *, const Layout &, int32_t *, cudaStream_t);
 int launch_mincurv_pdip(int, int, const int32_t *, double *, const Layout &, const PdipParams &, double *, int32_t *,
-                        int32_t *, int, cudaStream_t);
+                        int32_t *, int, int *, cudaStream_t);
 int launch_mincurv_pdip_kappa(int, int, const int32_t *, double *, const Layout &, const PdipParams &, double, double *,
-                              int32_t *, int32_t *, int, cudaStream_t);
+                              int32_t *, int32_t *, int, int *, cudaStream_t);
 void launch_mincurv_finalize(int, int, const int32_t *, double *, const Layout &, const double *, double, double *,
                              double *, int32_t *, cudaStream_t);
 void launch_calc_splines(int, int, const int32_t *, const double *, int, const double *, int, double *, double *,
@@ -78,10 +78,11 @@ int mc_calc_splines_batch(int B, int n_max, const int32_t *n_pts, const double *
 }
 
 // ------------------------------------------------------------------------------------------------
+static size_t mincurv_slabs_bytes(int B, int n_max) { return align256((size_t)B * mc::make_layout(n_max).stride * sizeof(double)); }
+
 size_t mc_mincurv_workspace_bytes(int B, int n_max) {
     if (B <= 0 || n_max < mc::N_MIN) return 0;
-    const mc::Layout L = mc::make_layout(n_max);
-    return align256((size_t)B * L.stride * sizeof(double));
+    return mincurv_slabs_bytes(B, n_max) + 256;      // + the work counter of the persistent solver kernels
 }
 
 static int mincurv_args(const char *who, int B, int n_max, void *workspace, size_t workspace_bytes) {
@@ -112,7 +113,7 @@ int mc_mincurv_pdip_batch(int B, int n_max, const int32_t *n_pts, double *alpha,
     if (rc) return rc;
     mc::PdipParams prm;
     prm.max_iter = 40;
-    prm.mu_rel = 1e-11;
+    prm.mu_rel = 1e-10;
     prm.rd_rel = 1e-8;
     prm.eta = 0.995;
     int dev = 0, sms = 148;
@@ -121,8 +122,9 @@ int mc_mincurv_pdip_batch(int B, int n_max, const int32_t *n_pts, double *alpha,
     const int per_sm = (int)((227 * 1024) / mc::pdip_smem_bytes());
     int grid = sms * (per_sm > 0 ? per_sm : 1);
     if (grid > B) grid = B;
+    int *counter = (int *)((char *)workspace + mincurv_slabs_bytes(B, n_max));
     if (mc::launch_mincurv_pdip(B, n_max, n_pts, (double *)workspace, mc::make_layout(n_max), prm, alpha, status, iters,
-                                grid, (cudaStream_t)stream) != 0) {
+                                grid, counter, (cudaStream_t)stream) != 0) {
         snprintf(g_err, sizeof(g_err), "mincurv_pdip_kernel: cudaFuncSetAttribute failed");
         return MC_ECUDA;
     }
@@ -177,8 +179,9 @@ int mc_mincurv_kappa_batch(int B, int n_max, const int32_t *n_pts, double kappa_
     const int per_sm = (int)((227 * 1024) / mc::pdip_smem_bytes());
     int grid = sms * (per_sm > 0 ? per_sm : 1);
     if (grid > B) grid = B;
+    int *counter = (int *)((char *)workspace + mincurv_slabs_bytes(B, n_max));
     if (mc::launch_mincurv_pdip_kappa(B, n_max, n_pts, (double *)workspace, mc::make_layout(n_max), prm, kappa_bound, alpha,
-                                      status, iters, grid, (cudaStream_t)stream) != 0) {
+                                      status, iters, grid, counter, (cudaStream_t)stream) != 0) {
         snprintf(g_err, sizeof(g_err), "mincurv_pdip_kappa_kernel: cudaFuncSetAttribute failed");
         return MC_ECUDA;
     }

@@ -88,10 +88,10 @@ struct PdShared {
     double Ts[32 * TP];              // T_I, row-major (upper triangular)
     double Fa[32 * TP];              // F_{I-1} -> FW_I -> F_I, row-major (updated in place)
     uint64_t full_bar[2], empty_bar[2];
-    double dinv[32];
     double vbuf[8][32];
     double red[32];
     int flag;
+    int next;          // next instance index (dynamic work distribution)
 };
 
 // 1/sqrt(d) for a positive, normal d: hardware seed (rsqrt.approx.f64, ~2^-23) + one cubically convergent
@@ -126,19 +126,27 @@ __device__ __forceinline__ bool chol_inv32(double *As, double *Li, int lane) {
     for (int J = 0; J < 4; ++J) {
         const int c0 = 8 * J;
         const long long tp0 = clock64();
-        // ---- (1) panel update on the tensor cores ----
+        // ---- (1) panel update on the tensor cores (row blocks I >= J are independent: issue them interleaved) ----
         if (J > 0) {
-#pragma unroll 1
-            for (int I = J; I < 4; ++I) {
-                double c2[2];
-                c2[0] = As[(c0 + 2 * q) * TP + 8 * I + g];
-                c2[1] = As[(c0 + 2 * q + 1) * TP + 8 * I + g];
-#pragma unroll 1
-                for (int ks = 0; ks < 2 * J; ++ks)          // k = 4 ks + q runs over the finished columns 0 .. 8J-1
-                    dmma(c2, -As[(4 * ks + q) * TP + 8 * I + g], As[(4 * ks + q) * TP + c0 + g]);
-                As[(c0 + 2 * q) * TP + 8 * I + g] = c2[0];
-                As[(c0 + 2 * q + 1) * TP + 8 * I + g] = c2[1];
+            double c2[4][2];
+#pragma unroll
+            for (int I = 0; I < 4; ++I) {
+                c2[I][0] = As[(c0 + 2 * q) * TP + 8 * I + g];
+                c2[I][1] = As[(c0 + 2 * q + 1) * TP + 8 * I + g];
             }
+#pragma unroll 1
+            for (int ks = 0; ks < 2 * J; ++ks) {          // k = 4 ks + q runs over the finished columns 0 .. 8J-1
+                const double b = As[(4 * ks + q) * TP + c0 + g];
+#pragma unroll
+                for (int I = 1; I < 4; ++I)               // (row block 0 is never below a panel J >= 1)
+                    if (I >= J) dmma(c2[I], -As[(4 * ks + q) * TP + 8 * I + g], b);
+            }
+#pragma unroll
+            for (int I = 1; I < 4; ++I)
+                if (I >= J) {
+                    As[(c0 + 2 * q) * TP + 8 * I + g] = c2[I][0];
+                    As[(c0 + 2 * q + 1) * TP + 8 * I + g] = c2[I][1];
+                }
             __syncwarp();
         }
         const long long tp1 = clock64();
@@ -207,29 +215,35 @@ __device__ __forceinline__ bool chol_inv32(double *As, double *Li, int lane) {
         }
     }
     const long long tq0 = clock64();
-    // ---- off-diagonal blocks of the inverse, by block distance ----
-#pragma unroll 1
+    // ---- off-diagonal blocks of the inverse, by block distance (blocks of one distance are independent) ----
+#pragma unroll
     for (int d = 1; d < 4; ++d) {
-#pragma unroll 1
+        double w2[3][2];
+#pragma unroll
         for (int J = 0; J + d < 4; ++J) {
             const int I = J + d;
-            double w2[2] = {0.0, 0.0};
-#pragma unroll 1
+            w2[J][0] = 0.0; w2[J][1] = 0.0;
+#pragma unroll
             for (int ks = 2 * J; ks < 2 * I; ++ks)       // k = 4 ks + q over blocks K = J .. I-1
-                dmma(w2, As[(4 * ks + q) * TP + 8 * I + g], Li[(4 * ks + q) * TP + 8 * J + g]);
-            *reinterpret_cast<double2 *>(&Li[(8 * I + g) * TP + 8 * J + 2 * q]) = make_double2(w2[0], w2[1]);
+                dmma(w2[J], As[(4 * ks + q) * TP + 8 * I + g], Li[(4 * ks + q) * TP + 8 * J + g]);
         }
+#pragma unroll
+        for (int J = 0; J + d < 4; ++J)
+            *reinterpret_cast<double2 *>(&Li[(8 * (J + d) + g) * TP + 8 * J + 2 * q]) = make_double2(w2[J][0], w2[J][1]);
         __syncwarp();
-#pragma unroll 1
+        double x2[3][2];
+#pragma unroll
         for (int J = 0; J + d < 4; ++J) {
             const int I = J + d;
             const double b0 = Li[(8 * I + q) * TP + 8 * J + g], b1 = Li[(8 * I + 4 + q) * TP + 8 * J + g];
-            double x2[2] = {0.0, 0.0};
-            dmma(x2, -Li[(8 * I + g) * TP + 8 * I + q], b0);
-            dmma(x2, -Li[(8 * I + g) * TP + 8 * I + 4 + q], b1);
-            __syncwarp();
-            *reinterpret_cast<double2 *>(&Li[(8 * I + g) * TP + 8 * J + 2 * q]) = make_double2(x2[0], x2[1]);
+            x2[J][0] = 0.0; x2[J][1] = 0.0;
+            dmma(x2[J], -Li[(8 * I + g) * TP + 8 * I + q], b0);
+            dmma(x2[J], -Li[(8 * I + g) * TP + 8 * I + 4 + q], b1);
         }
+        __syncwarp();
+#pragma unroll
+        for (int J = 0; J + d < 4; ++J)
+            *reinterpret_cast<double2 *>(&Li[(8 * (J + d) + g) * TP + 8 * J + 2 * q]) = make_double2(x2[J][0], x2[J][1]);
         __syncwarp();
     }
     if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_prof[2], (unsigned long long)(clock64() - tq0));
@@ -267,45 +281,35 @@ __device__ __noinline__ bool factor_chain(PdShared &sh, const double *__restrict
         // =========================== phase A ===========================
         const long long tA = clock64();
         if (I < nb) {
-            // ---- T_I T_I^T on the tensor cores first (lower 8x8 blocks) ... ----
-            double m2[10][2];
+            // the fill warps have put the band rows of this block into shared memory
+            if (I > 0) named_bar_sync(2, PD_THREADS);
+            // ---- A' = A_I + D_I - T_I T_I^T (lower 8x8 blocks): band gather + tensor cores, column-major into As ----
 #pragma unroll
-            for (int i = 0, bi = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j <= i; ++j, ++bi) {
-                    m2[bi][0] = 0.0; m2[bi][1] = 0.0;
+                for (int j = 0; j <= i; ++j) {
+                    double c2[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int r = 8 * i + g, c = 8 * j + 2 * q + e;
+                        const int lo = (c < r) ? c : r, dist = (c < r) ? r - c : c - r;
+                        double v = sh.band[lo * HB_PITCH + dist];
+                        const bool real = (base + r) < NA && (base + c) < NA;
+                        if (!real) v = (r == c) ? 1.0 : 0.0;
+                        else if (r == c) v += DD[base + r];
+                        c2[e] = v;
+                    }
                     if (I > 0) {
 #pragma unroll
                         for (int K = i; K < 4; ++K)      // T upper triangular: blocks (i,K), (j,K) nonzero for K >= i >= j
 #pragma unroll
                             for (int s = 0; s < 2; ++s)
-                                dmma(m2[bi], sh.Ts[(8 * i + g) * TP + 8 * K + 4 * s + q], sh.Ts[(8 * j + g) * TP + 8 * K + 4 * s + q]);
+                                dmma(c2, -sh.Ts[(8 * i + g) * TP + 8 * K + 4 * s + q], sh.Ts[(8 * j + g) * TP + 8 * K + 4 * s + q]);
                     }
-                }
-#pragma unroll
-            for (int i = 0, bi = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; ++j, ++bi) {
-                    sh.As[(8 * j + 2 * q) * TP + 8 * i + g] = -m2[bi][0];
-                    sh.As[(8 * j + 2 * q + 1) * TP + 8 * i + g] = -m2[bi][1];
+                    sh.As[(8 * j + 2 * q) * TP + 8 * i + g] = c2[0];
+                    sh.As[(8 * j + 2 * q + 1) * TP + 8 * i + g] = c2[1];
                 }
             if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_prof[15], (unsigned long long)(clock64() - tA));
-            // ---- ... then A' = A_I + D_I - T T^T once the band rows of this block are in shared memory ----
-            if (I > 0) named_bar_sync(2, PD_THREADS);
-            __syncwarp();
-            {   // lower triangle (lane = row r, columns c <= r): As[c][r] += band entry (+ D on the diagonal)
-                const int r = lane;
-                const bool rreal = (base + r) < NA;
-                const double dd = rreal ? DD[base + r] : 0.0;
-#pragma unroll 4
-                for (int c = 0; c < 32; ++c) {
-                    if (c <= r) {
-                        double v = rreal ? sh.band[c * HB_PITCH + (r - c)] : ((r == c) ? 1.0 : 0.0);   // c < r <= NA-1-base => column real
-                        if (c == r) v += dd;
-                        sh.As[c * TP + r] += v;
-                    }
-                }
-            }
         } else {
             named_bar_sync(3, PD_THREADS);      // the fill warps have put the separator Schur complement into As
         }
@@ -693,7 +697,7 @@ __device__ void band_matvec(const double *__restrict__ HB, const double *__restr
 __global__ void __launch_bounds__(PD_THREADS, 4)
 mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double *__restrict__ ws, Layout L,
                     PdipParams prm, double *__restrict__ alpha_out, int32_t *__restrict__ status,
-                    int32_t *__restrict__ iters_out) {
+                    int32_t *__restrict__ iters_out, int *__restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PdShared &sh = *reinterpret_cast<PdShared *>(smem_raw);
     if (threadIdx.x == 0) {
@@ -704,10 +708,15 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
     __syncthreads();
     unsigned fill = 0;      // ring fills so far (uniform across the CTA)
 
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    for (;;) {
+        // instances are handed out dynamically (iteration counts differ between instances)
+        __syncthreads();
+        if (threadIdx.x == 0) sh.next = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int b = sh.next;
+        if (b >= B) break;
         const int n = n_pts ? n_pts[b] : n_max;
         double *aout = alpha_out + (size_t)b * n_max;
-        __syncthreads();
         if (status[b] != 0) {
             for (int i = threadIdx.x; i < n_max; i += PD_THREADS) aout[i] = 0.0;
             if (iters_out && threadIdx.x == 0) iters_out[b] = 0;
@@ -877,7 +886,7 @@ int debug_read_profile(unsigned long long *host_out, int reset) {
 }
 
 int launch_mincurv_pdip(int B, int n_max, const int32_t *n_pts, double *ws, const Layout &L, const PdipParams &prm,
-                        double *alpha, int32_t *status, int32_t *iters, int grid, cudaStream_t stream) {
+                        double *alpha, int32_t *status, int32_t *iters, int grid, int *work_counter, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(mincurv_pdip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -885,7 +894,8 @@ int launch_mincurv_pdip(int B, int n_max, const int32_t *n_pts, double *ws, cons
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    mincurv_pdip_kernel<<<grid, PD_THREADS, sizeof(PdShared), stream>>>(B, n_max, n_pts, ws, L, prm, alpha, status, iters);
+    cudaMemsetAsync(work_counter, 0, sizeof(int), stream);
+    mincurv_pdip_kernel<<<grid, PD_THREADS, sizeof(PdShared), stream>>>(B, n_max, n_pts, ws, L, prm, alpha, status, iters, work_counter);
     return 0;
 }
 
@@ -900,7 +910,7 @@ int launch_mincurv_pdip(int B, int n_max, const int32_t *n_pts, double *ws, cons
 __global__ void __launch_bounds__(PD_THREADS, 4)
 mincurv_pdip_kappa_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double *__restrict__ ws, Layout L,
                           PdipParams prm, double kb, double *__restrict__ alpha_out, int32_t *__restrict__ status,
-                          int32_t *__restrict__ iters_out) {
+                          int32_t *__restrict__ iters_out, int *__restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PdShared &sh = *reinterpret_cast<PdShared *>(smem_raw);
     if (threadIdx.x == 0) {
@@ -910,8 +920,12 @@ mincurv_pdip_kappa_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, d
     }
     __syncthreads();
     unsigned fill = 0;
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    for (;;) {
         __syncthreads();
+        if (threadIdx.x == 0) sh.next = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int b = sh.next;
+        if (b >= B) break;
         if (status[b] != 4) continue;
         const int n = n_pts ? n_pts[b] : n_max;
         double *aout = alpha_out + (size_t)b * n_max;
@@ -1081,7 +1095,8 @@ mincurv_pdip_kappa_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, d
 }
 
 int launch_mincurv_pdip_kappa(int B, int n_max, const int32_t *n_pts, double *ws, const Layout &L, const PdipParams &prm,
-                              double kappa_bound, double *alpha, int32_t *status, int32_t *iters, int grid, cudaStream_t stream) {
+                              double kappa_bound, double *alpha, int32_t *status, int32_t *iters, int grid, int *work_counter,
+                              cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(mincurv_pdip_kappa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1089,8 +1104,9 @@ int launch_mincurv_pdip_kappa(int B, int n_max, const int32_t *n_pts, double *ws
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
+    cudaMemsetAsync(work_counter, 0, sizeof(int), stream);
     mincurv_pdip_kappa_kernel<<<grid, PD_THREADS, sizeof(PdShared), stream>>>(B, n_max, n_pts, ws, L, prm, kappa_bound, alpha,
-                                                                             status, iters);
+                                                                             status, iters, work_counter);
     return 0;
 }
 
