@@ -88,6 +88,7 @@ struct PdShared {
     double Ts[32 * TP];              // T_I, row-major (upper triangular)
     double Fa[32 * TP];              // F_{I-1} -> FW_I -> F_I, row-major (updated in place)
     uint64_t full_bar[2], empty_bar[2];
+    double rsv[32];                  // 1 / L[r][r] of the block being factored (warp 0 -> warp 1)
     double vbuf[8][32];
     double red[32];
     int flag;
@@ -106,6 +107,9 @@ __device__ __forceinline__ double fast_rsqrt(double d) {
     return fma(y * e, fma(0.375, e, 0.5), y);
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // Cholesky + explicit inverse of a 32x32 SPD block on 8x8 sub-blocks (one warp):
 //   A (lower triangle) column-major in As (As[c*TP + r]) -> L in As (lower), Linv = L^{-1} row-major in Li
@@ -119,7 +123,7 @@ __device__ __forceinline__ double fast_rsqrt(double d) {
 // Off-diagonal blocks of Linv, by block distance d = 1..3 (DMMA):  W = sum_{K=J}^{I-1} L_IK Linv_KJ,
 //   Linv_IJ = -Linv_II W   (W passes through its destination slot in Li to change fragment layout).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool chol_inv32(double *As, double *Li, int lane) {
+__device__ __forceinline__ bool chol_inv32(double *As, double *Li, double *rsv, int lane) {
     const int g = lane >> 2, q = lane & 3;
     bool ok = true;
 #pragma unroll 1
@@ -177,43 +181,21 @@ __device__ __forceinline__ bool chol_inv32(double *As, double *Li, int lane) {
 #pragma unroll
         for (int t = 0; t < 8; ++t)
             if (lane >= c0 + t) As[(c0 + t) * TP + lane] = a[t];
-        const long long tp2 = clock64();
-        // ---- (3) inverse of the diagonal block: X[v][t], v >= t  (dg[v][t] = L[v][t] for v > t, rs[t] = 1/L[t][t]) ----
-        // computed redundantly in every lane; lane (g, q) then stores row g, columns 2q, 2q+1 of the 8x8 block
-        // (selected with branch-free selects: a lane-indexed switch would diverge 32 ways)
-        double e0 = 0.0, e1 = 0.0;
+        // ---- (3) the inverse of the 8x8 diagonal block is computed by warp 1 (off this warp's critical path):
+        //      publish 1/L[t][t], make the panel visible, signal ----
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            double x[8];
-            x[t] = rs[t];
-#pragma unroll
-            for (int v = t + 1; v < 8; ++v) {
-                double acc = 0.0;
-#pragma unroll
-                for (int u = t; u < v; ++u) acc = fma(dg[v][u], x[u], acc);
-                x[v] = -acc * rs[v];
-            }
-#pragma unroll
-            for (int v = t; v < 8; ++v) {
-                const bool mine = (g == v) && (q == (t >> 1));
-                if (t & 1) e1 = mine ? x[v] : e1;
-                else e0 = mine ? x[v] : e0;
-            }
-        }
-        *reinterpret_cast<double2 *>(&Li[(c0 + g) * TP + c0 + 2 * q]) = make_double2(e0, e1);
-        // zero the blocks of Li to the right of the diagonal block (rows c0..c0+7, columns c0+8..31)
-        for (int e = lane; e < 8 * (24 - c0); e += 32) {
-            const int rr = e / (24 - c0), cc = e - rr * (24 - c0);
-            Li[(c0 + rr) * TP + c0 + 8 + cc] = 0.0;
-        }
+        for (int t = 0; t < 8; ++t)
+            if (lane == t) rsv[c0 + t] = rs[t];
         __syncwarp();
+        __threadfence_block();
+        named_bar_arrive(4, 64);
         if (blockIdx.x == 0 && lane == 0) {
             const long long tp3 = clock64();
             atomicAdd(&g_prof[13], (unsigned long long)(tp1 - tp0));
-            atomicAdd(&g_prof[14], (unsigned long long)(tp2 - tp1));
-            atomicAdd(&g_prof[8], (unsigned long long)(tp3 - tp2));
+            atomicAdd(&g_prof[14], (unsigned long long)(tp3 - tp1));
         }
     }
+    named_bar_sync(5, 64);        // warp 1 has written the four diagonal blocks of Linv (and the zeros right of them)
     const long long tq0 = clock64();
     // ---- off-diagonal blocks of the inverse, by block distance (blocks of one distance are independent) ----
 #pragma unroll
@@ -250,6 +232,53 @@ __device__ __forceinline__ bool chol_inv32(double *As, double *Li, int lane) {
     return ok;
 }
 
+
+// Warp 1's share of chol_inv32: for every panel J (signalled by warp 0 on named barrier 4) the inverse of the 8x8
+// diagonal block of L, redundantly in every lane from broadcast loads, stored to Li with the zeros to its right.
+__device__ __forceinline__ void local_inverses(const double *As, double *Li, const double *rsv, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll 1
+    for (int J = 0; J < 4; ++J) {
+        const int c0 = 8 * J;
+        named_bar_sync(4, 64);
+        double dg[8][8], rs[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            rs[v] = rsv[c0 + v];
+#pragma unroll
+            for (int w = 0; w < v; ++w) dg[v][w] = As[(c0 + w) * TP + c0 + v];
+        }
+        double e0 = 0.0, e1 = 0.0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            double x[8];
+            x[t] = rs[t];
+#pragma unroll
+            for (int v = t + 1; v < 8; ++v) {
+                double acc = 0.0;
+#pragma unroll
+                for (int u = t; u < v; ++u) acc = fma(dg[v][u], x[u], acc);
+                x[v] = -acc * rs[v];
+            }
+#pragma unroll
+            for (int v = t; v < 8; ++v) {
+                const bool mine = (g == v) && (q == (t >> 1));
+                if (t & 1) e1 = mine ? x[v] : e1;
+                else e0 = mine ? x[v] : e0;
+            }
+        }
+        *reinterpret_cast<double2 *>(&Li[(c0 + g) * TP + c0 + 2 * q]) = make_double2(e0, e1);
+        // zero the blocks of Li to the right of the diagonal block (rows c0..c0+7, columns c0+8..31)
+        for (int e = lane; e < 8 * (24 - c0); e += 32) {
+            const int rr = e / (24 - c0), cc = e - rr * (24 - c0);
+            Li[(c0 + rr) * TP + c0 + 8 + cc] = 0.0;
+        }
+    }
+    __syncwarp();
+    __threadfence_block();
+    named_bar_arrive(5, 64);
+}
+
 // S[own 16 rows][:] -= F[own rows][:] F^T  (rolled over the four 8-wide k blocks to keep the code small)
 __device__ __forceinline__ void s_update(double (&sacc)[2][4][2], const double *Ft, int ib, int g, int q) {
 #pragma unroll 1
@@ -266,8 +295,6 @@ __device__ __forceinline__ void s_update(double (&sacc)[2][4][2], const double *
     }
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // ---- warp 0: the chain.  Rounds I = 0..nb-1 are the chain blocks, round nb the separator block. ----
 __device__ __noinline__ bool factor_chain(PdShared &sh, const double *__restrict__ DD, double *__restrict__ tiles, int n, int nb) {
@@ -315,7 +342,7 @@ __device__ __noinline__ bool factor_chain(PdShared &sh, const double *__restrict
         }
         __syncwarp();
         const long long tB = clock64();
-        ok = chol_inv32(sh.As, sh.Li, lane) && ok;
+        ok = chol_inv32(sh.As, sh.Li, sh.rsv, lane) && ok;
         const long long tC = clock64();
         const long long tD = tC;
         if (blockIdx.x == 0 && lane == 0) {
@@ -398,6 +425,7 @@ __device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict_
                 }
             __syncwarp();
             named_bar_arrive(3, PD_THREADS);
+            if (warp == 1) local_inverses(sh.As, sh.Li, sh.rsv, lane);
         } else {
             // hand the prefetched band rows of this block to warp 0, then prefetch the next block's
             if (I > 0) {
@@ -449,6 +477,7 @@ __device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict_
                     *reinterpret_cast<double2 *>(&Ft[(8 * (ib + i) + g) * TP + 8 * j + 2 * q]) = make_double2(c2[0], c2[1]);
                 }
             }
+            if (warp == 1) local_inverses(sh.As, sh.Li, sh.rsv, lane);
         }
         __syncthreads();
         // =========================== phase B ===========================
