@@ -139,6 +139,10 @@ def run_b200(args) -> dict:
         if timed_kernels:
             ev["pdip"][-1][1].record()
         _lib.check(lib.mc_mincurv_finalize_batch(Bq, n, None, p(alpha), KAPPA_BOUND, p(cerr), p(kmax), p(st), p(ws), ws.numel(), s), "finalize")
+        # curvature-row phase for the instances the box-only phase flagged (none on this workload: the kernel scans the
+        # status words and returns) + re-evaluation -- together the five launches of mc_mincurv_solve_batch
+        _lib.check(lib.mc_mincurv_kappa_batch(Bq, n, None, KAPPA_BOUND, p(alpha), p(st), p(iters), p(ws), ws.numel(), s), "kappa")
+        _lib.check(lib.mc_mincurv_finalize_batch(Bq, n, None, p(alpha), KAPPA_BOUND, p(cerr), p(kmax), p(st), p(ws), ws.numel(), s), "finalize")
         rl = B_.create_raceline_batch(rt_dev, nv, alpha, STEP_INTERP, n_out_max=n_out_max, with_head_curv=True)
         return dict(alpha=alpha, status=st, iters=iters, kappa=rl["kappa"], raceline=rl["raceline_interp"], n_out=rl["n_out"])
 
@@ -229,7 +233,7 @@ def run_b200(args) -> dict:
         "clocks": clocks,
         "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": int(host_pinned.numel() * 8),
                 "d2h_bytes_per_step": int(alpha_host.numel() * 8 + status_host.numel() * 4)},
-        "gpu_launches": 5 * args.steps,
+        "gpu_launches": 7 * args.steps,
         "roofline": {"bound": "hbm", "kernel": "mincurv_pdip_kernel", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",

@@ -1,6 +1,7 @@
 // extern "C" boundary of libmincurv_b200.so -- see include/mincurv_b200.h for the contract and the
 // reference call sites each entry point replaces.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/mincurv_b200.h"
@@ -119,7 +120,11 @@ int mc_mincurv_pdip_batch(int B, int n_max, const int32_t *n_pts, double *alpha,
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int per_sm = (int)((227 * 1024) / mc::pdip_smem_bytes());
+    int per_sm = (int)((227 * 1024) / mc::pdip_smem_bytes());
+    if (const char *e = getenv("MC_DEBUG_PDIP_CTAS_PER_SM")) {      // occupancy experiments only (tools/prof_run.py)
+        const int v = atoi(e);
+        if (v > 0 && v < per_sm) per_sm = v;
+    }
     int grid = sms * (per_sm > 0 ? per_sm : 1);
     if (grid > B) grid = B;
     int *counter = (int *)((char *)workspace + mincurv_slabs_bytes(B, n_max));

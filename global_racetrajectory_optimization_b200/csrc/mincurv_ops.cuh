@@ -9,12 +9,14 @@ namespace mc {
 constexpr int BD = 34;               // B_t band: offsets d = c' - c in [0, 34]
 constexpr int BB_T = BD + 1;         // 35 doubles per weight
 static_assert(3 * BB_T <= ZB_PITCH, "B band does not fit the slab pitch");
+__host__ __device__ constexpr int hband_win_doubles(int threads) { return 8 * (threads + BD + 1); }
 
 
 // Band of H_w = E^T diag(1 + wk) E into the slab's HB (wk == nullptr: plain H = E^T E).
-// Uses V_T0..V_T5 and the B-band scratch; ends with the band written but NOT synchronised.
-__device__ inline void assemble_hband(double *slab, const Layout &L, int n, const double *__restrict__ wk) {
-    const double *H = vec(slab, L, V_H), *TII = vec(slab, L, V_TII), *RHOP = vec(slab, L, V_RHOP), *RHOM = vec(slab, L, V_RHOM);
+// Uses V_T0..V_T5 and the B-band scratch; win: shared scratch of hband_win_doubles(blockDim.x) doubles.
+// Ends with the band written but NOT synchronised.
+__device__ inline void assemble_hband(double *slab, const Layout &L, int n, const double *__restrict__ wk, double *win) {
+    const double *IH = vec(slab, L, V_IH), *TII = vec(slab, L, V_TII), *RHOP = vec(slab, L, V_RHOP), *RHOM = vec(slab, L, V_RHOM);
     const double *NX = vec(slab, L, V_NX), *NY = vec(slab, L, V_NY), *SX = vec(slab, L, V_SX), *SY = vec(slab, L, V_SY);
     // ---- P6: tail sums U_t (towards +), V_t (towards -) of the three weights, chunked with warm-up ----
     double *U0 = vec(slab, L, V_T0), *U1 = vec(slab, L, V_T1), *U2 = vec(slab, L, V_T2);
@@ -44,37 +46,48 @@ __device__ inline void assemble_hband(double *slab, const Layout &L, int n, cons
         }
     }
     __syncthreads();
-    // ---- P7: band of B_t[c][c + d], d = 0..34 ----
+    // ---- P7: band of B_t[c][c + d], d = 0..34.  One thread per row c, a serial recurrence along d that reads
+    //      eight vectors at c + d: a sliding window, staged in shared memory per chunk of blockDim.x rows (from
+    //      global memory the 34 dependent steps ran at L2 latency and were 56 % of the assembly kernel) ----
     double *BB = slab + L.o_zb;
-    for (int c = threadIdx.x; c < n; c += blockDim.x) {
-        double *row = BB + (size_t)c * ZB_PITCH;
-        const double tc = TII[c];
-        const double v0 = V0[c], v1 = V1[c], v2 = V2[c];
-        {
-            const double ww = wk ? 1.0 + wk[c] : 1.0;
-            const double sx = SX[c], sy = SY[c], t2 = tc * tc;
-            row[0] = t2 * (U0[c] + v0 - ww * sy * sy);
-            row[BB_T] = t2 * (U1[c] + v1 - ww * sx * sy);
-            row[2 * BB_T] = t2 * (U2[c] + v2 - ww * sx * sx);
-        }
-        double P = tc, m0 = 0.0, m1 = 0.0, m2 = 0.0;
-        int cp = c;
-        for (int d = 1; d <= BD; ++d) {
-            const int cprev = cp;
-            cp = (cp + 1 == n) ? 0 : cp + 1;
-            const double rp = RHOP[cp];
-            if (d >= 2) {
-                const double ww = wk ? 1.0 + wk[cprev] : 1.0;
-                const double sx = SX[cprev], sy = SY[cprev], pt = ww * P * TII[cprev];
-                m0 = rp * fma(sy * sy, pt, m0);
-                m1 = rp * fma(sx * sy, pt, m1);
-                m2 = rp * fma(sx * sx, pt, m2);
+    {
+        const int CH = blockDim.x, WL = CH + BD + 1;
+        double *w_rp = win, *w_ti = win + WL, *w_u0 = win + 2 * WL, *w_u1 = win + 3 * WL, *w_u2 = win + 4 * WL;
+        double *w_yy = win + 5 * WL, *w_xy = win + 6 * WL, *w_xx = win + 7 * WL;     // ww sy^2 t, ww sx sy t, ww sx^2 t
+        for (int cbase = 0; cbase < n; cbase += CH) {
+            __syncthreads();
+            for (int e = threadIdx.x; e < WL; e += blockDim.x) {
+                const int idx = (cbase + e) % n;
+                const double ww = wk ? 1.0 + wk[idx] : 1.0;
+                const double sx = SX[idx], sy = SY[idx], ti = TII[idx], wt = ww * ti;
+                w_rp[e] = RHOP[idx]; w_ti[e] = ti; w_u0[e] = U0[idx]; w_u1[e] = U1[idx]; w_u2[e] = U2[idx];
+                w_yy[e] = sy * sy * wt; w_xy[e] = sx * sy * wt; w_xx[e] = sx * sx * wt;
             }
-            P *= rp;
-            const double tp = TII[cp];
-            row[d] = P * fma(tp, U0[cp], tc * v0) + m0;
-            row[BB_T + d] = P * fma(tp, U1[cp], tc * v1) + m1;
-            row[2 * BB_T + d] = P * fma(tp, U2[cp], tc * v2) + m2;
+            __syncthreads();
+            const int c = cbase + threadIdx.x, l = threadIdx.x;
+            if (c < n) {
+                double *row = BB + (size_t)c * ZB_PITCH;
+                const double tc = w_ti[l];
+                const double v0 = V0[c], v1 = V1[c], v2 = V2[c];
+                row[0] = tc * (tc * (w_u0[l] + v0) - w_yy[l]);
+                row[BB_T] = tc * (tc * (w_u1[l] + v1) - w_xy[l]);
+                row[2 * BB_T] = tc * (tc * (w_u2[l] + v2) - w_xx[l]);
+                double P = tc, m0 = 0.0, m1 = 0.0, m2 = 0.0;
+#pragma unroll 2
+                for (int d = 1; d <= BD; ++d) {
+                    const double rp = w_rp[l + d];
+                    if (d >= 2) {
+                        m0 = rp * fma(w_yy[l + d - 1], P, m0);
+                        m1 = rp * fma(w_xy[l + d - 1], P, m1);
+                        m2 = rp * fma(w_xx[l + d - 1], P, m2);
+                    }
+                    P *= rp;
+                    const double tp = w_ti[l + d];
+                    row[d] = P * fma(tp, w_u0[l + d], tc * v0) + m0;
+                    row[BB_T + d] = P * fma(tp, w_u1[l + d], tc * v1) + m1;
+                    row[2 * BB_T + d] = P * fma(tp, w_u2[l + d], tc * v2) + m2;
+                }
+            }
         }
     }
     __syncthreads();
@@ -85,7 +98,7 @@ __device__ inline void assemble_hband(double *slab, const Layout &L, int n, cons
         const int i = e / (HBW + 1), k = e - i * (HBW + 1);
         int j = i + k; if (j >= n) j -= n;
         const int im1 = (i == 0) ? n - 1 : i - 1, jm1 = (j == 0) ? n - 1 : j - 1;
-        const double ihi = 1.0 / H[i], ihim = 1.0 / H[im1], ihj = 1.0 / H[j], ihjm = 1.0 / H[jm1];
+        const double ihi = IH[i], ihim = IH[im1], ihj = IH[j], ihjm = IH[jm1];
         const double ei[3] = {ihim, -(ihim + ihi), ihi};       // 6 D2[c][i] / 6, c = i-1, i, i+1
         const double ej[3] = {ihjm, -(ihjm + ihj), ihj};
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;

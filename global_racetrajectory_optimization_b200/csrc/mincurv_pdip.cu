@@ -29,8 +29,8 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int PD_THREADS = 96;
 constexpr int TP = 36;             // shared tile pitch (doubles): conflict-free DMMA fragment loads
 constexpr int LTP = 33;            // pitch of the packed (Linv | T) tile in HBM
-constexpr int LT_TILE = 32 * LTP;  // 1056 doubles
-constexpr int F_TILE = 32 * LTP;   // F_I, row-major pitch 33 (odd pitch: conflict-free lane=row and lane=column access)
+constexpr int LT_TILE = 32 * LTP;  // packed (Linv lower | T upper, shifted one column right)
+constexpr int F_TILE = 32 * LTP;   // F_I, row-major
 constexpr int BLK_TILES = LT_TILE + F_TILE;   // doubles per chain block in the slab (one contiguous bulk copy)
 constexpr unsigned BLK_BYTES = BLK_TILES * sizeof(double);
 constexpr unsigned LT_BYTES = LT_TILE * sizeof(double);
@@ -75,7 +75,7 @@ __device__ __forceinline__ double hentry(const double *HB, int n, int i, int j) 
 }
 
 // Phase cycle counters of CTA 0 / warp 0 (debug aid, read with mc_debug_read_profile): cheap enough to stay compiled in.
-__device__ unsigned long long g_prof[16];
+__device__ unsigned long long g_prof[24];
 #define PROF_T0() const long long _pt0 = (blockIdx.x == 0 && (threadIdx.x & 31) == 0) ? clock64() : 0
 #define PROF_ADD(slot, t0) do { if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_prof[slot], (unsigned long long)(clock64() - (t0))); } while (0)
 
@@ -87,8 +87,8 @@ struct PdShared {
     double Li[32 * TP];              // Linv_I, row-major
     double Ts[32 * TP];              // T_I, row-major (upper triangular)
     double Fa[32 * TP];              // F_{I-1} -> FW_I -> F_I, row-major (updated in place)
-    uint64_t full_bar[2], empty_bar[2];
-    double rsv[32];                  // 1 / L[r][r] of the block being factored (warp 0 -> warp 1)
+    uint64_t full_bar[2], empty_bar[2], aux_bar[2];
+    double xch[2][32];               // sweeps: y_I (forward) / F_I^T x_S (backward) exchanged between warps 0 and 2 per ring stage
     double vbuf[8][32];
     double red[32];
     int flag;
@@ -123,7 +123,7 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm vol
 // Off-diagonal blocks of Linv, by block distance d = 1..3 (DMMA):  W = sum_{K=J}^{I-1} L_IK Linv_KJ,
 //   Linv_IJ = -Linv_II W   (W passes through its destination slot in Li to change fragment layout).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool chol_inv32(double *As, double *Li, double *rsv, int lane) {
+__device__ __forceinline__ bool chol_inv32(double *As, double *Li, int lane) {
     const int g = lane >> 2, q = lane & 3;
     bool ok = true;
 #pragma unroll 1
@@ -181,21 +181,43 @@ __device__ __forceinline__ bool chol_inv32(double *As, double *Li, double *rsv, 
 #pragma unroll
         for (int t = 0; t < 8; ++t)
             if (lane >= c0 + t) As[(c0 + t) * TP + lane] = a[t];
-        // ---- (3) the inverse of the 8x8 diagonal block is computed by warp 1 (off this warp's critical path):
-        //      publish 1/L[t][t], make the panel visible, signal ----
+        const long long tp2 = clock64();
+        // ---- (3) inverse of the diagonal block: X[v][t], v >= t  (dg[v][t] = L[v][t] for v > t, rs[t] = 1/L[t][t]) ----
+        // computed redundantly in every lane; lane (g, q) then stores row g, columns 2q, 2q+1 of the 8x8 block
+        // (selected with branch-free selects: a lane-indexed switch would diverge 32 ways)
+        double e0 = 0.0, e1 = 0.0;
 #pragma unroll
-        for (int t = 0; t < 8; ++t)
-            if (lane == t) rsv[c0 + t] = rs[t];
+        for (int t = 0; t < 8; ++t) {
+            double x[8];
+            x[t] = rs[t];
+#pragma unroll
+            for (int v = t + 1; v < 8; ++v) {
+                double acc = 0.0;
+#pragma unroll
+                for (int u = t; u < v; ++u) acc = fma(dg[v][u], x[u], acc);
+                x[v] = -acc * rs[v];
+            }
+#pragma unroll
+            for (int v = t; v < 8; ++v) {
+                const bool mine = (g == v) && (q == (t >> 1));
+                if (t & 1) e1 = mine ? x[v] : e1;
+                else e0 = mine ? x[v] : e0;
+            }
+        }
+        *reinterpret_cast<double2 *>(&Li[(c0 + g) * TP + c0 + 2 * q]) = make_double2(e0, e1);
+        // zero the blocks of Li to the right of the diagonal block (rows c0..c0+7, columns c0+8..31)
+        for (int e = lane; e < 8 * (24 - c0); e += 32) {
+            const int rr = e / (24 - c0), cc = e - rr * (24 - c0);
+            Li[(c0 + rr) * TP + c0 + 8 + cc] = 0.0;
+        }
         __syncwarp();
-        __threadfence_block();
-        named_bar_arrive(4, 64);
         if (blockIdx.x == 0 && lane == 0) {
             const long long tp3 = clock64();
             atomicAdd(&g_prof[13], (unsigned long long)(tp1 - tp0));
-            atomicAdd(&g_prof[14], (unsigned long long)(tp3 - tp1));
+            atomicAdd(&g_prof[14], (unsigned long long)(tp2 - tp1));
+            atomicAdd(&g_prof[8], (unsigned long long)(tp3 - tp2));
         }
     }
-    named_bar_sync(5, 64);        // warp 1 has written the four diagonal blocks of Linv (and the zeros right of them)
     const long long tq0 = clock64();
     // ---- off-diagonal blocks of the inverse, by block distance (blocks of one distance are independent) ----
 #pragma unroll
@@ -232,53 +254,6 @@ __device__ __forceinline__ bool chol_inv32(double *As, double *Li, double *rsv, 
     return ok;
 }
 
-
-// Warp 1's share of chol_inv32: for every panel J (signalled by warp 0 on named barrier 4) the inverse of the 8x8
-// diagonal block of L, redundantly in every lane from broadcast loads, stored to Li with the zeros to its right.
-__device__ __forceinline__ void local_inverses(const double *As, double *Li, const double *rsv, int lane) {
-    const int g = lane >> 2, q = lane & 3;
-#pragma unroll 1
-    for (int J = 0; J < 4; ++J) {
-        const int c0 = 8 * J;
-        named_bar_sync(4, 64);
-        double dg[8][8], rs[8];
-#pragma unroll
-        for (int v = 0; v < 8; ++v) {
-            rs[v] = rsv[c0 + v];
-#pragma unroll
-            for (int w = 0; w < v; ++w) dg[v][w] = As[(c0 + w) * TP + c0 + v];
-        }
-        double e0 = 0.0, e1 = 0.0;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            double x[8];
-            x[t] = rs[t];
-#pragma unroll
-            for (int v = t + 1; v < 8; ++v) {
-                double acc = 0.0;
-#pragma unroll
-                for (int u = t; u < v; ++u) acc = fma(dg[v][u], x[u], acc);
-                x[v] = -acc * rs[v];
-            }
-#pragma unroll
-            for (int v = t; v < 8; ++v) {
-                const bool mine = (g == v) && (q == (t >> 1));
-                if (t & 1) e1 = mine ? x[v] : e1;
-                else e0 = mine ? x[v] : e0;
-            }
-        }
-        *reinterpret_cast<double2 *>(&Li[(c0 + g) * TP + c0 + 2 * q]) = make_double2(e0, e1);
-        // zero the blocks of Li to the right of the diagonal block (rows c0..c0+7, columns c0+8..31)
-        for (int e = lane; e < 8 * (24 - c0); e += 32) {
-            const int rr = e / (24 - c0), cc = e - rr * (24 - c0);
-            Li[(c0 + rr) * TP + c0 + 8 + cc] = 0.0;
-        }
-    }
-    __syncwarp();
-    __threadfence_block();
-    named_bar_arrive(5, 64);
-}
-
 // S[own 16 rows][:] -= F[own rows][:] F^T  (rolled over the four 8-wide k blocks to keep the code small)
 __device__ __forceinline__ void s_update(double (&sacc)[2][4][2], const double *Ft, int ib, int g, int q) {
 #pragma unroll 1
@@ -296,94 +271,61 @@ __device__ __forceinline__ void s_update(double (&sacc)[2][4][2], const double *
 }
 
 
-// ---- warp 0: the chain.  Rounds I = 0..nb-1 are the chain blocks, round nb the separator block. ----
-__device__ __noinline__ bool factor_chain(PdShared &sh, const double *__restrict__ DD, double *__restrict__ tiles, int n, int nb) {
+// ---- one 8-row block of  X Linv^T  (Linv lower triangular: k blocks K <= j), in place in the shared tile X and
+//      to the HBM tile gx (pitch LTP).  Used for F_I = FW_I Linv_I^T. ----
+__device__ __forceinline__ void rowblock_times_linvT(double *X, const double *Li, double *__restrict__ gx, int rb, int g, int q) {
+    double a[8];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) a[ks] = X[(8 * rb + g) * TP + 4 * ks + q];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        double c2[2] = {0.0, 0.0};
+#pragma unroll
+        for (int K = 0; K <= j; ++K)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) dmma(c2, a[2 * K + s], Li[(8 * j + g) * TP + 8 * K + 4 * s + q]);
+        const int r = 8 * rb + g, c = 8 * j + 2 * q;
+        *reinterpret_cast<double2 *>(&X[r * TP + c]) = make_double2(c2[0], c2[1]);
+        gx[r * LTP + c] = c2[0];
+        gx[r * LTP + c + 1] = c2[1];
+    }
+}
+
+// ---- warp 0: the chain.  Rounds I = 0..nb-1 are the chain blocks, round nb the separator block.
+//      Phase A: Cholesky + inverse of the block the fill warps assembled into As.
+//      Phase B: Linv_I and F_I = FW_I Linv_I^T to the HBM tiles (the fill warps build T_{I+1} and A'_{I+1}). ----
+__device__ __noinline__ bool factor_chain(PdShared &sh, double *__restrict__ tiles, int n, int nb) {
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
-    const int NA = n - 32;
     bool ok = true;
-    __syncthreads();                      // fill warps have picked up the separator block from As
+    __syncthreads();                      // the fill warps have assembled A'_0 into As
     for (int I = 0; I <= nb; ++I) {
-        const int base = 32 * I;
         // =========================== phase A ===========================
         const long long tA = clock64();
-        if (I < nb) {
-            // the fill warps have put the band rows of this block into shared memory
-            if (I > 0) named_bar_sync(2, PD_THREADS);
-            // ---- A' = A_I + D_I - T_I T_I^T (lower 8x8 blocks): band gather + tensor cores, column-major into As ----
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; ++j) {
-                    double c2[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int r = 8 * i + g, c = 8 * j + 2 * q + e;
-                        const int lo = (c < r) ? c : r, dist = (c < r) ? r - c : c - r;
-                        double v = sh.band[lo * HB_PITCH + dist];
-                        const bool real = (base + r) < NA && (base + c) < NA;
-                        if (!real) v = (r == c) ? 1.0 : 0.0;
-                        else if (r == c) v += DD[base + r];
-                        c2[e] = v;
-                    }
-                    if (I > 0) {
-#pragma unroll
-                        for (int K = i; K < 4; ++K)      // T upper triangular: blocks (i,K), (j,K) nonzero for K >= i >= j
-#pragma unroll
-                            for (int s = 0; s < 2; ++s)
-                                dmma(c2, -sh.Ts[(8 * i + g) * TP + 8 * K + 4 * s + q], sh.Ts[(8 * j + g) * TP + 8 * K + 4 * s + q]);
-                    }
-                    sh.As[(8 * j + 2 * q) * TP + 8 * i + g] = c2[0];
-                    sh.As[(8 * j + 2 * q + 1) * TP + 8 * i + g] = c2[1];
-                }
-            if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_prof[15], (unsigned long long)(clock64() - tA));
-        } else {
-            named_bar_sync(3, PD_THREADS);      // the fill warps have put the separator Schur complement into As
-        }
-        __syncwarp();
+        if (I == nb) named_bar_sync(3, PD_THREADS);      // the fill warps have put the separator Schur complement into As
         const long long tB = clock64();
-        ok = chol_inv32(sh.As, sh.Li, sh.rsv, lane) && ok;
+        ok = chol_inv32(sh.As, sh.Li, lane) && ok;
         const long long tC = clock64();
-        const long long tD = tC;
         if (blockIdx.x == 0 && lane == 0) {
             atomicAdd(&g_prof[0], (unsigned long long)(tB - tA));
             atomicAdd(&g_prof[1], (unsigned long long)(tC - tB));
         }
         __syncthreads();
         const long long tE = clock64();
-        PROF_ADD(3, tD);
+        PROF_ADD(3, tC);
         // =========================== phase B ===========================
         {
-            // Linv_I -> packed HBM tile (lower part, row-major pitch 33); round nb: the separator's slot
+            // Linv_I -> packed HBM tile (lower part, row-major pitch LTP); round nb: the separator's slot
             double *gt = tiles + (size_t)I * BLK_TILES;
 #pragma unroll 4
             for (int r = 0; r < 32; ++r)
                 if (lane <= r) gt[r * LTP + lane] = sh.Li[r * TP + lane];
-            if (I + 1 < nb) {
-                // ---- T_{I+1} = B_I Linv_I^T : upper-triangular blocks (i <= j), K = i..j ----
-                double *gn = tiles + (size_t)(I + 1) * BLK_TILES;
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        double c2[2] = {0.0, 0.0};
-                        if (j >= i) {
-#pragma unroll
-                            for (int K = i; K <= j; ++K)
-#pragma unroll
-                                for (int s = 0; s < 2; ++s) {
-                                    // B_I[r][k] = M[base+32+r][base+k] = band[k][32 + r - k] for r <= k
-                                    const int r = 8 * i + g, k = 8 * K + 4 * s + q;
-                                    double av = 0.0;
-                                    if (r <= k && (base + 32 + r) < NA) av = sh.band[k * HB_PITCH + 32 + r - k];
-                                    dmma(c2, av, sh.Li[(8 * j + g) * TP + k]);
-                                }
-                        }
-                        const int r = 8 * i + g, c = 8 * j + 2 * q;
-                        *reinterpret_cast<double2 *>(&sh.Ts[r * TP + c]) = make_double2(c2[0], c2[1]);
-                        if (c >= r) gn[r * LTP + c + 1] = c2[0];
-                        if (c + 1 >= r) gn[r * LTP + c + 2] = c2[1];
-                    }
+            if (I < nb) {
+                // ---- F_I = FW_I Linv_I^T, in place in the shared F tile and to HBM ----
+                double *gf = gt + LT_TILE;
+#pragma unroll 1
+                for (int rb = 0; rb < 4; ++rb) rowblock_times_linvT(sh.Fa, sh.Li, gf, rb, g, q);
             }
         }
         const long long tS2 = clock64();
@@ -394,14 +336,69 @@ __device__ __noinline__ bool factor_chain(PdShared &sh, const double *__restrict
     return ok;
 }
 
-// ---- warps 1, 2: the two 16-row halves of the separator fill row (F, S) + band prefetch for warp 0 ----
-__device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict__ HB, double *__restrict__ tiles, int n, int nb) {
+// ---- fill warps, phase B: A'_J = A_J + D_J - T_J T_J^T (lower 8x8 blocks of row block i) from the staged band rows
+//      of block J (diagonal already carries D) and the T tile, column-major into As ----
+template <int i>
+__device__ __forceinline__ void assemble_rowblock(PdShared &sh, int baseJ, int NA, bool hasT, int g, int q) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+        double c2[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int r = 8 * i + g, c = 8 * j + 2 * q + e;
+            const int lo = (c < r) ? c : r, dist = (c < r) ? r - c : c - r;
+            double v = sh.band[lo * HB_PITCH + dist];
+            const bool real = (baseJ + r) < NA && (baseJ + c) < NA;
+            if (!real) v = (r == c) ? 1.0 : 0.0;
+            c2[e] = v;
+        }
+        if (hasT) {
+#pragma unroll
+            for (int K = i; K < 4; ++K)      // T upper triangular: blocks (i,K), (j,K) nonzero for K >= i >= j
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+                    dmma(c2, -sh.Ts[(8 * i + g) * TP + 8 * K + 4 * s + q], sh.Ts[(8 * j + g) * TP + 8 * K + 4 * s + q]);
+        }
+        sh.As[(8 * j + 2 * q) * TP + 8 * i + g] = c2[0];
+        sh.As[(8 * j + 2 * q + 1) * TP + 8 * i + g] = c2[1];
+    }
+}
+
+// ---- fill warps, phase B: row block i of T_{I+1} = B_I Linv_I^T (upper-triangular blocks j >= i, K = i..j) into Ts and
+//      the HBM tile gn of block I+1 (shifted one column right, next to that block's Linv) ----
+template <int i>
+__device__ __forceinline__ void coupling_rowblock(PdShared &sh, double *__restrict__ gn, int base, int NA, int g, int q) {
+#pragma unroll
+    for (int j = i; j < 4; ++j) {
+        double c2[2] = {0.0, 0.0};
+#pragma unroll
+        for (int K = i; K <= j; ++K)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                // B_I[r][k] = M[base+32+r][base+k] = band[k][32 + r - k] for r <= k
+                const int r = 8 * i + g, k = 8 * K + 4 * s + q;
+                double av = 0.0;
+                if (r <= k && (base + 32 + r) < NA) av = sh.band[k * HB_PITCH + 32 + r - k];
+                dmma(c2, av, sh.Li[(8 * j + g) * TP + k]);
+            }
+        const int r = 8 * i + g, c = 8 * j + 2 * q;
+        *reinterpret_cast<double2 *>(&sh.Ts[r * TP + c]) = make_double2(c2[0], c2[1]);
+        if (c >= r) gn[r * LTP + c + 1] = c2[0];
+        if (c + 1 >= r) gn[r * LTP + c + 2] = c2[1];
+    }
+}
+
+// ---- warps 1, 2: the two 16-row halves of the separator fill row (FW, S) in phase A; in phase B the coupling block
+//      T_{I+1}, the band rows of block I+1 and the next diagonal block A'_{I+1} (so warp 0 only ever factors) ----
+__device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict__ HB, const double *__restrict__ DD,
+                                        double *__restrict__ tiles, int n, int nb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int NA = n - 32;
     const int ib = 2 * (warp - 1);
     double sacc[2][4][2];          // own 16 rows of the separator Schur complement (C fragments)
     double breg[17];               // half of the next block's band rows (1088 doubles = 2 x 32 x 17)
+    double dreg = 0.0;             // ... and of its barrier diagonal D (lanes 0..15: one row each)
     double *Ft = sh.Fa;
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -409,6 +406,17 @@ __device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict_
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) sacc[i][j][e] = sh.As[(8 * j + 2 * q + e) * TP + 8 * (ib + i) + g];
+    named_bar_sync(1, 64);         // both fill warps have picked the separator block up: As is free
+    // A'_0 (no coupling term) from the band rows of block 0 staged by factor(); prefetch the rows of block 1
+    if (warp == 1) { assemble_rowblock<0>(sh, 0, NA, false, g, q); assemble_rowblock<1>(sh, 0, NA, false, g, q); }
+    else           { assemble_rowblock<2>(sh, 0, NA, false, g, q); assemble_rowblock<3>(sh, 0, NA, false, g, q); }
+    if (1 < nb) {
+        const double *src = HB + (size_t)32 * HB_PITCH + (warp - 1) * 544;
+#pragma unroll
+        for (int t = 0; t < 17; ++t) breg[t] = src[32 * t + lane];
+        const int nd = 32 + 16 * (warp - 1) + lane;
+        dreg = (lane < 16 && nd < NA) ? DD[nd] : 0.0;
+    }
     __syncthreads();
     for (int I = 0; I <= nb; ++I) {
         const int base = 32 * I;
@@ -425,20 +433,7 @@ __device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict_
                 }
             __syncwarp();
             named_bar_arrive(3, PD_THREADS);
-            if (warp == 1) local_inverses(sh.As, sh.Li, sh.rsv, lane);
         } else {
-            // hand the prefetched band rows of this block to warp 0, then prefetch the next block's
-            if (I > 0) {
-#pragma unroll
-                for (int t = 0; t < 17; ++t) sh.band[(warp - 1) * 544 + 32 * t + lane] = breg[t];
-                __syncwarp();
-                named_bar_arrive(2, PD_THREADS);
-            }
-            if (I + 1 < nb) {
-                const double *src = HB + (size_t)(base + 32) * HB_PITCH + (warp - 1) * 544;
-#pragma unroll
-                for (int t = 0; t < 17; ++t) breg[t] = src[32 * t + lane];
-            }
             // ---- S -= F_{I-1} F_{I-1}^T (own 16 rows, reads the whole F tile) ----
             if (I > 0) s_update(sacc, Ft, ib, g, q);
             // ---- FW = Y_I - F_{I-1} T_I^T, in place in the F tile (own rows) ----
@@ -477,33 +472,30 @@ __device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict_
                     *reinterpret_cast<double2 *>(&Ft[(8 * (ib + i) + g) * TP + 8 * j + 2 * q]) = make_double2(c2[0], c2[1]);
                 }
             }
-            if (warp == 1) local_inverses(sh.As, sh.Li, sh.rsv, lane);
         }
         __syncthreads();
         // =========================== phase B ===========================
-        if (I < nb) {
-            // ---- F_I = FW Linv_I^T (own rows; Linv lower triangular: K <= j), in place ----
-            double a[2][8];
+        if (I + 1 < nb) {
+            // ---- T_{I+1} = B_I Linv_I^T (band rows of block I, coupling part) ----
+            double *gn = tiles + (size_t)(I + 1) * BLK_TILES;
+            if (warp == 1) coupling_rowblock<0>(sh, gn, base, NA, g, q);
+            else { coupling_rowblock<1>(sh, gn, base, NA, g, q); coupling_rowblock<2>(sh, gn, base, NA, g, q); coupling_rowblock<3>(sh, gn, base, NA, g, q); }
+            named_bar_sync(1, 64);       // T complete; nobody reads the band rows of block I any more
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) a[i][ks] = Ft[(8 * (ib + i) + g) * TP + 4 * ks + q];
+            for (int t = 0; t < 17; ++t) sh.band[(warp - 1) * 544 + 32 * t + lane] = breg[t];
             __syncwarp();
-            double *gf = tiles + (size_t)I * BLK_TILES + LT_TILE;
+            if (lane < 16) sh.band[(warp - 1) * 544 + lane * HB_PITCH] += dreg;      // + barrier diagonal D
+            named_bar_sync(1, 64);       // band rows of block I+1 staged
+            if (I + 2 < nb) {
+                const double *src = HB + (size_t)(base + 64) * HB_PITCH + (warp - 1) * 544;
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    double c2[2] = {0.0, 0.0};
-#pragma unroll
-                    for (int K = 0; K <= j; ++K)
-#pragma unroll
-                        for (int s = 0; s < 2; ++s) dmma(c2, a[i][2 * K + s], sh.Li[(8 * j + g) * TP + 8 * K + 4 * s + q]);
-                    const int r = 8 * (ib + i) + g, c = 8 * j + 2 * q;
-                    *reinterpret_cast<double2 *>(&Ft[r * TP + c]) = make_double2(c2[0], c2[1]);
-                    gf[r * LTP + c] = c2[0];
-                    gf[r * LTP + c + 1] = c2[1];
-                }
+                for (int t = 0; t < 17; ++t) breg[t] = src[32 * t + lane];
+                const int nd = base + 64 + 16 * (warp - 1) + lane;
+                dreg = (lane < 16 && nd < NA) ? DD[nd] : 0.0;
+            }
+            // ---- A'_{I+1} = A + D - T T^T ----
+            if (warp == 1) { assemble_rowblock<0>(sh, base + 32, NA, true, g, q); assemble_rowblock<1>(sh, base + 32, NA, true, g, q); }
+            else           { assemble_rowblock<2>(sh, base + 32, NA, true, g, q); assemble_rowblock<3>(sh, base + 32, NA, true, g, q); }
         }
         __syncthreads();
     }
@@ -522,12 +514,17 @@ __device__ __noinline__ bool factor(PdShared &sh, const double *__restrict__ HB,
         sh.As[c * TP + r] = v;
     }
     // band rows of block 0
-    for (int e = threadIdx.x; e < 32 * HB_PITCH; e += PD_THREADS) sh.band[e] = HB[e];
+    for (int e = threadIdx.x; e < 32 * HB_PITCH; e += PD_THREADS) {
+        const int r = e / HB_PITCH;
+        double v = HB[e];
+        if (e == r * HB_PITCH && r < NA) v += DD[r];           // diagonal: H_ii + D_i
+        sh.band[e] = v;
+    }
     __syncthreads();
     if (warp == 0) {
-        if (!factor_chain(sh, DD, tiles, n, nb)) sh.flag = 1;
+        if (!factor_chain(sh, tiles, n, nb)) sh.flag = 1;
     } else {
-        factor_fill(sh, HB, tiles, n, nb);
+        factor_fill(sh, HB, DD, tiles, n, nb);
     }
     __syncthreads();
     return sh.flag == 0;
@@ -608,8 +605,9 @@ __device__ __forceinline__ double sm_f_mtv(const double *F, const double *v, int
 // ------------------------------------------------------------------------------------------------
 // solve M x = g with the stored factor.  g, x: real-indexed vectors (length n) in the slab; ypad: padded scratch.
 // The 2 nb + 1 factor blocks [0 .. nb-1, S, nb-1 .. 0] are streamed HBM -> shared by one elected thread of
-// warp 3 with cp.async.bulk (TMA, one 16.5 KB copy per block) into a two-stage ring guarded by full/empty
-// mbarriers; warp 0 consumes them: per block three 32x32 mat-vecs from shared memory.
+// warp 1 with cp.async.bulk (TMA, one 16.5 KB copy per block) into a two-stage ring guarded by full/empty
+// mbarriers; warp 0 runs the chain recurrences (two triangular 32x32 mat-vecs per block from shared memory),
+// warp 2 the separator-row products F_I y_I / F_I^T x_S next to it.
 // `fill` counts the ring fills of this CTA so far (parity bookkeeping); the new count is returned.
 // ------------------------------------------------------------------------------------------------
 __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ tiles, const double *__restrict__ g,
@@ -618,9 +616,11 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
     const int NA = n - 32;
     double *stage0 = sh.As;
     const unsigned nfill = 2u * nb + 1u;
+    double *tb = sh.vbuf[1], *xb = sh.vbuf[0], *xs = sh.vbuf[3], *gsum = sh.vbuf[4];
     fence_proxy_async();        // the staging area was last written through the generic proxy (factor tiles)
     __syncthreads();
     if (warp == 1) {
+        // ---- producer: one elected thread issues the bulk copies ----
         if (lane == 0) {
             for (unsigned i = 0; i < nfill; ++i) {
                 const unsigned f = fill + i, st = f & 1u, k = f >> 1;
@@ -631,13 +631,38 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
                 tma_load_1d(stage0 + st * BLK_TILES, tiles + (size_t)blk * BLK_TILES, bytes, &sh.full_bar[st]);
             }
         }
-    } else if (warp == 0) {
-        double *yb = sh.vbuf[0], *tb = sh.vbuf[1], *xs = sh.vbuf[3];
-        // ---- forward: y_I = Linv_I (g_I - T_I y_{I-1}),  gS -= F_I y_I ----
+    } else if (warp == 2) {
+        // ---- separator-row mat-vecs, off the chain: forward gS -= F_I y_I (one block behind warp 0),
+        //      backward c_I = F_I^T x_S (ahead of warp 0).  aux_bar[st] hands y_I / c_I over per ring fill. ----
         double gacc = 0.0;
-        double gnext = (lane < NA) ? g[lane] : 0.0;
-        yb[lane] = 0.0;
+        for (int I = 0; I < nb; ++I) {
+            const unsigned f = fill + I, st = f & 1u, k = f >> 1;
+            mbar_wait(&sh.full_bar[st], k & 1u);
+            mbar_wait(&sh.aux_bar[st], k & 1u);
+            gacc += sm_f_mv(stage0 + st * BLK_TILES + LT_TILE, sh.xch[st], lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.empty_bar[st]);
+        }
+        gsum[lane] = gacc;
         __syncwarp();
+        named_bar_arrive(9, 64);
+        {
+            const unsigned f = fill + nb, st = f & 1u, k = f >> 1;
+            mbar_wait(&sh.full_bar[st], k & 1u);
+            mbar_wait(&sh.aux_bar[st], k & 1u);          // x_S is in xs
+            if (lane == 0) mbar_arrive(&sh.empty_bar[st]);
+        }
+        for (int i = 0; i < nb; ++i) {
+            const unsigned f = fill + nb + 1 + i, st = f & 1u, k = f >> 1;
+            mbar_wait(&sh.full_bar[st], k & 1u);
+            sh.xch[st][lane] = sm_f_mtv(stage0 + st * BLK_TILES + LT_TILE, xs, lane);
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&sh.aux_bar[st]); mbar_arrive(&sh.empty_bar[st]); }
+        }
+    } else {
+        // ---- forward: y_I = Linv_I (g_I - T_I y_{I-1}) ----
+        const long long tfw = clock64();
+        double gnext = (lane < NA) ? g[lane] : 0.0;
         for (int I = 0; I < nb; ++I) {
             const unsigned f = fill + I, st = f & 1u, k = f >> 1;
             const double gv = gnext;
@@ -645,38 +670,45 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
             const long long tw = clock64();
             mbar_wait(&sh.full_bar[st], k & 1u);
             PROF_ADD(7, tw);
-            const double *LT = stage0 + st * BLK_TILES, *Ft = LT + LT_TILE;
+            const long long t1 = clock64();
+            const double *LT = stage0 + st * BLK_TILES;
             double v = gv;
-            if (I > 0) v -= sm_t_mv(LT, yb, lane);
-            __syncwarp();
+            if (I > 0) v -= sm_t_mv(LT, sh.xch[st ^ 1u], lane);
             tb[lane] = v;
             __syncwarp();
+            PROF_ADD(16, t1);
+            const long long t2 = clock64();
             const double y = sm_linv_mv(LT, tb, lane);
-            yb[lane] = y;
+            sh.xch[st][lane] = y;
+            PROF_ADD(17, t2);
+            const long long t3 = clock64();
             ypad[32 * I + lane] = y;
             __syncwarp();
-            gacc += sm_f_mv(Ft, yb, lane);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sh.empty_bar[st]);
+            if (lane == 0) { mbar_arrive(&sh.aux_bar[st]); mbar_arrive(&sh.empty_bar[st]); }
+            PROF_ADD(18, t3);
         }
+        PROF_ADD(21, tfw);
+        const long long tsep = clock64();
         // ---- separator: x_S = LinvS^T LinvS (g_S - sum F_I y_I) ----
         {
             const unsigned f = fill + nb, st = f & 1u, k = f >> 1;
-            const double gs = g[NA + lane] - gacc;
+            const double gs0 = g[NA + lane];
             mbar_wait(&sh.full_bar[st], k & 1u);
+            named_bar_sync(9, 64);
             const double *LS = stage0 + st * BLK_TILES;
-            tb[lane] = gs;
+            tb[lane] = gs0 - gsum[lane];
             __syncwarp();
             const double ys = sm_linv_mv(LS, tb, lane);
+            xb[lane] = ys;
             __syncwarp();
-            yb[lane] = ys;
-            __syncwarp();
-            const double xv = sm_linv_mtv(LS, yb, lane);
+            const double xv = sm_linv_mtv(LS, xb, lane);
             xs[lane] = xv;
             x[NA + lane] = xv;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sh.empty_bar[st]);
+            if (lane == 0) { mbar_arrive(&sh.aux_bar[st]); mbar_arrive(&sh.empty_bar[st]); }
         }
+        PROF_ADD(22, tsep);
+        const long long tbw = clock64();
         // ---- backward: x_I = Linv_I^T (y_I - F_I^T x_S - T_{I+1}^T x_{I+1}) ----
         double u = 0.0;                               // (T_{I+1}^T x_{I+1})[lane]
         double ynext = ypad[32 * (nb - 1) + lane];
@@ -685,22 +717,26 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
             const unsigned f = fill + nb + 1 + i, st = f & 1u, k = f >> 1;
             const double yv = ynext;
             if (I > 0) ynext = ypad[32 * (I - 1) + lane];
+            const long long tw = clock64();
             mbar_wait(&sh.full_bar[st], k & 1u);
-            const double *LT = stage0 + st * BLK_TILES, *Ft = LT + LT_TILE;
-            const double v = yv - sm_f_mtv(Ft, xs, lane) - u;
-            __syncwarp();
-            tb[lane] = v;
+            mbar_wait(&sh.aux_bar[st], k & 1u);
+            PROF_ADD(19, tw);
+            const double *LT = stage0 + st * BLK_TILES;
+            tb[lane] = yv - sh.xch[st][lane] - u;
             __syncwarp();
             const double xv = sm_linv_mtv(LT, tb, lane);
-            yb[lane] = xv;
+            xb[lane] = xv;
             if (32 * I + lane < NA) x[32 * I + lane] = xv;
             __syncwarp();
-            u = (I > 0) ? sm_t_mtv(LT, yb, lane) : 0.0;
+            u = (I > 0) ? sm_t_mtv(LT, xb, lane) : 0.0;
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh.empty_bar[st]);
         }
+        PROF_ADD(20, tbw);
     }
+    const long long tend = clock64();
     __syncthreads();
+    PROF_ADD(23, tend);
     return fill + nfill;
 }
 
@@ -731,7 +767,8 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
     PdShared &sh = *reinterpret_cast<PdShared *>(smem_raw);
     if (threadIdx.x == 0) {
         mbar_init(&sh.full_bar[0], 1); mbar_init(&sh.full_bar[1], 1);
-        mbar_init(&sh.empty_bar[0], 1); mbar_init(&sh.empty_bar[1], 1);
+        mbar_init(&sh.empty_bar[0], 2); mbar_init(&sh.empty_bar[1], 2);
+        mbar_init(&sh.aux_bar[0], 1); mbar_init(&sh.aux_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -906,9 +943,9 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
 size_t pdip_smem_bytes() { return sizeof(PdShared); }
 
 int debug_read_profile(unsigned long long *host_out, int reset) {
-    if (cudaMemcpyFromSymbol(host_out, g_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(host_out, g_prof, sizeof(unsigned long long) * 24) != cudaSuccess) return -1;
     if (reset) {
-        unsigned long long z[16] = {0};
+        unsigned long long z[24] = {0};
         if (cudaMemcpyToSymbol(g_prof, z, sizeof(z)) != cudaSuccess) return -1;
     }
     return 0;
@@ -944,7 +981,8 @@ mincurv_pdip_kappa_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, d
     PdShared &sh = *reinterpret_cast<PdShared *>(smem_raw);
     if (threadIdx.x == 0) {
         mbar_init(&sh.full_bar[0], 1); mbar_init(&sh.full_bar[1], 1);
-        mbar_init(&sh.empty_bar[0], 1); mbar_init(&sh.empty_bar[1], 1);
+        mbar_init(&sh.empty_bar[0], 2); mbar_init(&sh.empty_bar[1], 2);
+        mbar_init(&sh.aux_bar[0], 1); mbar_init(&sh.aux_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -1015,7 +1053,7 @@ mincurv_pdip_kappa_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, d
                 VV[i] = (kl - KR[i]) + l3 * rp3 / s3 - l4 * rp4 / s4;       // affine: t3 = -s3 l3, t4 = -s4 l4
             }
             __syncthreads();
-            assemble_hband(slab, L, n, WK);
+            assemble_hband(slab, L, n, WK, sh.As);     // the tile area is free between the sweeps and the next factorisation
             __syncthreads();
             apply_Et(slab, L, n, VV, ETV, t0, t1, t2, t3, t4, t5);
             for (int i = threadIdx.x; i < n; i += PD_THREADS) RHS[i] = -F[i] - ETV[i];

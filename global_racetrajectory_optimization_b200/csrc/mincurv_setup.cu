@@ -30,6 +30,7 @@ mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
     const int n = n_pts ? n_pts[b] : n_max;
     double *slab = ws + (size_t)b * L.stride;
     __shared__ int s_flag;
+    __shared__ double s_win[hband_win_doubles(256)];      // sliding windows of the B-band recurrence (assemble_hband)
     if (threadIdx.x == 0) s_flag = 0;
     __syncthreads();
     if (n < N_MIN || n > n_max) {
@@ -49,7 +50,7 @@ mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
     double *SX = vec(slab, L, V_SX), *SY = vec(slab, L, V_SY), *KREF = vec(slab, L, V_KREF);
     double *LB = vec(slab, L, V_LB), *UB = vec(slab, L, V_UB), *F = vec(slab, L, V_F);
     double *T0 = vec(slab, L, V_T0), *T1 = vec(slab, L, V_T1), *T2 = vec(slab, L, V_T2), *T3 = vec(slab, L, V_T3);
-    double *T4 = vec(slab, L, V_T4), *T5 = vec(slab, L, V_T5);
+    double *T4 = vec(slab, L, V_T4), *T5 = vec(slab, L, V_T5), *IH = vec(slab, L, V_IH);
 
     // ---- P1: coalesced, vectorised load of the reftrack rows [x, y, w_r, w_l] (32 B per point) ----
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -60,6 +61,7 @@ mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
         const double hi = hb[i], him = hb[im1];
         PX[i] = xy.x; PY[i] = xy.y; NX[i] = nn.x; NY[i] = nn.y;
         H[i] = hi;
+        IH[i] = 1.0 / hi;
         DG[i] = 2.0 * (him + hi);
         double ub = ww.x - 0.5 * wv;          // dev_max_right
         double lb = -(ww.y - 0.5 * wv);       // -dev_max_left
@@ -115,7 +117,7 @@ mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
         F[i] = F_SCALE * (NY[i] * zy - NX[i] * zx);
     }
     __syncthreads();
-    assemble_hband(slab, L, n, nullptr);
+    assemble_hband(slab, L, n, nullptr, s_win);
     double *HB = slab + L.o_hb;
     for (int i = threadIdx.x; i < n; i += blockDim.x) HB[(size_t)i * HB_PITCH + HBW + 1] = 0.0;
     if (threadIdx.x == 0) status[b] = 0;

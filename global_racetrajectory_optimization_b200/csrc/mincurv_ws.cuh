@@ -18,6 +18,7 @@ enum Vec : int {
     V_ALPHA, V_LU, V_LL, V_RD, V_RHS, V_DX, V_DD, V_DLU, V_DLL, V_SU, V_SL,
     V_ISU, V_ISL, V_YPAD,                                   // reciprocal slacks, padded forward-solve vector
     V_S3, V_S4, V_L3, V_L4, V_KL, V_WK, V_EDX, V_T3K, V_T4K, V_VV,   // curvature-row phase (K2b')
+    V_IH,                                                   // 1 / h
     NUM_VEC
 };
 

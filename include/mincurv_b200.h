@@ -164,9 +164,9 @@ int mc_iqp_relinearise_batch(int B, int n_max, const int32_t *n_pts, const int32
  * `alpha *= iter / iters_min` of tph.iqp_handler. */
 int mc_scale_alpha_batch(int B, int n_max, double *alpha, const double *scale_batch, double scale, void *stream);
 
-/* Debug aid (synchronous): reads (and optionally clears) 16 cycle counters that CTA 0 of mincurv_pdip_kernel
+/* Debug aid (synchronous): reads (and optionally clears) 24 cycle counters that CTA 0 of mincurv_pdip_kernel
  * accumulates per phase -- used by tools/prof_run.py to attribute time inside the kernel. Host pointer. */
-int mc_debug_read_profile(unsigned long long *host_out16, int reset);
+int mc_debug_read_profile(unsigned long long *host_out24, int reset);
 
 #ifdef __cplusplus
 }

@@ -20,9 +20,9 @@ print("prof_run", Bn, N, f"{dt*1e3:.2f} ms {Bn/dt:.0f} QP/s status", np.bincount
 
 import ctypes
 from global_racetrajectory_optimization_b200 import _lib
-buf = (ctypes.c_ulonglong * 16)()
+buf = (ctypes.c_ulonglong * 24)()
 _lib.load().mc_debug_read_profile(ctypes.cast(buf, ctypes.c_void_p), 1)
-names = ["Aasm", "chol_inv", "ci_offdiag", "barA", "phaseB", "barB", "solves", "tma_wait", "ci_locinv", "total", "factor", "nqp", "iters", "ci_dmma_upd", "ci_panel", "Aasm_dmma"]
+names = ["Aasm", "chol_inv", "ci_offdiag", "barA", "phaseB", "barB", "solves", "tma_wait", "ci_locinv", "total", "factor", "nqp", "iters", "ci_dmma_upd", "ci_panel", "Aasm_dmma", "fw_tmv", "fw_linv", "fw_tail", "bw_wait", "bw_loop", "fw_loop", "sep", "solve_end"]
 vals = list(buf)
 nq = max(vals[11], 1)
 print("profile (cycles per QP of CTA 0, %d QPs, %.1f iters/QP):" % (vals[11], vals[12] / nq))
