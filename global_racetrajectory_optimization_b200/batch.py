@@ -35,7 +35,7 @@ SLAB_VECTORS = ("H DIAG DFW DBW LFW INVD TII RHOP RHOM PX PY NX NY MX MY XP YP S
                 "T0 T1 T2 T3 T4 T5 ALPHA LU LL RD RHS DX DD DLU DLL SU SL ISU ISL YPAD "
                 "S3 S4 L3 L4 KL WK EDX T3K T4K VV IH").split()
 HB_PITCH = 34
-ZB_PITCH = 106
+ZB_PITCH = 108
 
 
 def mincurv_slab_layout(n_max: int) -> dict:

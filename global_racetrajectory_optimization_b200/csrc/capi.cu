@@ -117,6 +117,9 @@ int mc_mincurv_pdip_batch(int B, int n_max, const int32_t *n_pts, double *alpha,
     prm.mu_rel = 1e-10;
     prm.rd_rel = 1e-8;
     prm.eta = 0.995;
+    prm.dx_rel = 1e-5;
+    if (const char *e = getenv("MC_DEBUG_PDIP_DX_REL")) { const double v = atof(e); if (v >= 0.0) prm.dx_rel = v; }
+    if (const char *e = getenv("MC_DEBUG_PDIP_MU_REL")) { const double v = atof(e); if (v > 0.0) prm.mu_rel = v; }   // tolerance experiments only
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -178,6 +181,7 @@ int mc_mincurv_kappa_batch(int B, int n_max, const int32_t *n_pts, double kappa_
     prm.mu_rel = 1e-11;
     prm.rd_rel = 1e-8;
     prm.eta = 0.995;
+    prm.dx_rel = 0.0;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

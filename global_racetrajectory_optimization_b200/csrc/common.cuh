@@ -17,7 +17,7 @@ namespace mc {
 
 constexpr int TRI_CHUNK = 8;     // points per thread in the chunked recurrences
 constexpr int TRI_WARM = 56;     // warm-up length of the periodic recurrences
-constexpr int ZB_PITCH = 106;    // per-point scratch row of the assembly: three B_t bands of 35 entries (mincurv_setup.cu)
+constexpr int ZB_PITCH = 108;    // per-point scratch row of the assembly: three B_t bands of 35 entries at pitch 36 (sector-aligned runs)
 constexpr int HBW = 32;          // half-bandwidth kept of H = E^T E (truncation error ~1e-10 on alpha)
 constexpr int HB_PITCH = 34;     // 33 used, padded so that a row is a multiple of 16 bytes
 constexpr int N_MIN = 80;        // smallest supported closed track (band must not wrap onto itself)

@@ -7,9 +7,10 @@
 namespace mc {
 
 constexpr int BD = 34;               // B_t band: offsets d = c' - c in [0, 34]
-constexpr int BB_T = BD + 1;         // 35 doubles per weight
+constexpr int BB_T = BD + 2;         // 35 doubles per weight, pitch 36: runs of four offsets are 32 B sectors
 static_assert(3 * BB_T <= ZB_PITCH, "B band does not fit the slab pitch");
-__host__ __device__ constexpr int hband_win_doubles(int threads) { return 8 * (threads + BD + 1); }
+constexpr int STG_T = 32 * 5;         // per-warp store staging: [row][4 offsets], padded to 5
+__host__ __device__ constexpr int hband_win_doubles(int threads) { return 8 * (threads + BD + 1) + (threads / 32) * 3 * STG_T; }
 
 
 // Band of H_w = E^T diag(1 + wk) E into the slab's HB (wk == nullptr: plain H = E^T E).
@@ -64,29 +65,49 @@ __device__ inline void assemble_hband(double *slab, const Layout &L, int n, cons
                 w_yy[e] = sy * sy * wt; w_xy[e] = sx * sy * wt; w_xx[e] = sx * sx * wt;
             }
             __syncthreads();
-            const int c = cbase + threadIdx.x, l = threadIdx.x;
-            if (c < n) {
-                double *row = BB + (size_t)c * ZB_PITCH;
-                const double tc = w_ti[l];
-                const double v0 = V0[c], v1 = V1[c], v2 = V2[c];
-                row[0] = tc * (tc * (w_u0[l] + v0) - w_yy[l]);
-                row[BB_T] = tc * (tc * (w_u1[l] + v1) - w_xy[l]);
-                row[2 * BB_T] = tc * (tc * (w_u2[l] + v2) - w_xx[l]);
-                double P = tc, m0 = 0.0, m1 = 0.0, m2 = 0.0;
-#pragma unroll 2
-                for (int d = 1; d <= BD; ++d) {
-                    const double rp = w_rp[l + d];
-                    if (d >= 2) {
-                        m0 = rp * fma(w_yy[l + d - 1], P, m0);
-                        m1 = rp * fma(w_xy[l + d - 1], P, m1);
-                        m2 = rp * fma(w_xx[l + d - 1], P, m2);
+            // every lane runs the recurrence (rows past n compute on window data and are masked at the store);
+            // the results leave through a per-warp staging tile so that a store instruction writes 8 rows x 32 B
+            // (8 sectors) instead of 32 rows x 8 B (32 sectors): the direct stores were LSU-tag bound
+            const int c = cbase + threadIdx.x, l = threadIdx.x, lane = threadIdx.x & 31;
+            double *stg = win + 8 * WL + (threadIdx.x >> 5) * 3 * STG_T;
+            const int cw = cbase + (threadIdx.x & ~31);           // first row of this warp
+            const double tc = w_ti[l];
+            const double v0 = (c < n) ? V0[c] : 0.0, v1 = (c < n) ? V1[c] : 0.0, v2 = (c < n) ? V2[c] : 0.0;
+            stg[lane * 5] = tc * (tc * (w_u0[l] + v0) - w_yy[l]);
+            stg[STG_T + lane * 5] = tc * (tc * (w_u1[l] + v1) - w_xy[l]);
+            stg[2 * STG_T + lane * 5] = tc * (tc * (w_u2[l] + v2) - w_xx[l]);
+            double P = tc, m0 = 0.0, m1 = 0.0, m2 = 0.0;
+#pragma unroll 1
+            for (int d0 = 0; d0 <= BD; d0 += 4) {
+#pragma unroll
+                for (int s = (d0 == 0) ? 1 : 0; s < 4; ++s) {
+                    const int d = d0 + s;
+                    if (d <= BD) {
+                        const double rp = w_rp[l + d];
+                        if (d >= 2) {
+                            m0 = rp * fma(w_yy[l + d - 1], P, m0);
+                            m1 = rp * fma(w_xy[l + d - 1], P, m1);
+                            m2 = rp * fma(w_xx[l + d - 1], P, m2);
+                        }
+                        P *= rp;
+                        const double tp = w_ti[l + d];
+                        stg[lane * 5 + s] = P * fma(tp, w_u0[l + d], tc * v0) + m0;
+                        stg[STG_T + lane * 5 + s] = P * fma(tp, w_u1[l + d], tc * v1) + m1;
+                        stg[2 * STG_T + lane * 5 + s] = P * fma(tp, w_u2[l + d], tc * v2) + m2;
                     }
-                    P *= rp;
-                    const double tp = w_ti[l + d];
-                    row[d] = P * fma(tp, w_u0[l + d], tc * v0) + m0;
-                    row[BB_T + d] = P * fma(tp, w_u1[l + d], tc * v1) + m1;
-                    row[2 * BB_T + d] = P * fma(tp, w_u2[l + d], tc * v2) + m2;
                 }
+                __syncwarp();
+                const int s = lane & 3;
+                if (d0 + s <= BD) {
+#pragma unroll
+                    for (int t = 0; t < 3; ++t)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int r = (lane >> 2) + 8 * k;
+                            if (cw + r < n) BB[(size_t)(cw + r) * ZB_PITCH + t * BB_T + d0 + s] = stg[t * STG_T + r * 5 + s];
+                        }
+                }
+                __syncwarp();
             }
         }
     }

@@ -58,6 +58,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     }
 }
+// same, for waits that are not on the chain's critical path (TMA producer, warp 2): back off between probes --
+// a bare try_wait loop re-issues every ~8 cycles (ncu: 14 % of all executed instructions were these probes,
+// each one a shared-memory transaction competing with warp 0)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, unsigned parity) {
+    unsigned ok = 0;
+    for (;;) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(32);
+    }
+}
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -624,7 +636,7 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
         if (lane == 0) {
             for (unsigned i = 0; i < nfill; ++i) {
                 const unsigned f = fill + i, st = f & 1u, k = f >> 1;
-                if (k > 0) mbar_wait(&sh.empty_bar[st], (k - 1) & 1u);
+                if (k > 0) mbar_wait_relaxed(&sh.empty_bar[st], (k - 1) & 1u);
                 const unsigned blk = (i < (unsigned)nb) ? i : ((i == (unsigned)nb) ? (unsigned)nb : 2u * nb - i);
                 const unsigned bytes = (i == (unsigned)nb) ? LT_BYTES : BLK_BYTES;
                 mbar_expect_tx(&sh.full_bar[st], bytes);
@@ -637,8 +649,8 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
         double gacc = 0.0;
         for (int I = 0; I < nb; ++I) {
             const unsigned f = fill + I, st = f & 1u, k = f >> 1;
-            mbar_wait(&sh.full_bar[st], k & 1u);
-            mbar_wait(&sh.aux_bar[st], k & 1u);
+            mbar_wait_relaxed(&sh.full_bar[st], k & 1u);
+            mbar_wait_relaxed(&sh.aux_bar[st], k & 1u);
             gacc += sm_f_mv(stage0 + st * BLK_TILES + LT_TILE, sh.xch[st], lane);
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh.empty_bar[st]);
@@ -648,13 +660,13 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
         named_bar_arrive(9, 64);
         {
             const unsigned f = fill + nb, st = f & 1u, k = f >> 1;
-            mbar_wait(&sh.full_bar[st], k & 1u);
-            mbar_wait(&sh.aux_bar[st], k & 1u);          // x_S is in xs
+            mbar_wait_relaxed(&sh.full_bar[st], k & 1u);
+            mbar_wait_relaxed(&sh.aux_bar[st], k & 1u);          // x_S is in xs
             if (lane == 0) mbar_arrive(&sh.empty_bar[st]);
         }
         for (int i = 0; i < nb; ++i) {
             const unsigned f = fill + nb + 1 + i, st = f & 1u, k = f >> 1;
-            mbar_wait(&sh.full_bar[st], k & 1u);
+            mbar_wait_relaxed(&sh.full_bar[st], k & 1u);
             sh.xch[st][lane] = sm_f_mtv(stage0 + st * BLK_TILES + LT_TILE, xs, lane);
             __syncwarp();
             if (lane == 0) { mbar_arrive(&sh.aux_bar[st]); mbar_arrive(&sh.empty_bar[st]); }
@@ -909,7 +921,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             rdl = block_reduce<1>(rdl, sh.red);
             ap = (prm.eta < rp) ? prm.eta / rp : 1.0;       // min(1, eta / max-ratio)
             ad = (prm.eta < rdl) ? prm.eta / rdl : 1.0;
-            double musum2 = 0.0, rdmax = 0.0;
+            double musum2 = 0.0, rdmax = 0.0, dxmax = 0.0, amax = 0.0;
 #pragma unroll 2
     #pragma unroll 1
         for (int i = threadIdx.x; i < n; i += PD_THREADS) {
@@ -923,10 +935,19 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
                 ISU[i] = 1.0 / sun; ISL[i] = 1.0 / sln;
                 musum2 += sun * lun + sln * lln;
                 rdmax = fmax(rdmax, fabs(rdn));
+                dxmax = fmax(dxmax, fabs(dx));
+                amax = fmax(amax, fabs(an));
             }
             mu = block_reduce<0>(musum2, sh.red) / (2.0 * n);
             rdmax = block_reduce<1>(rdmax, sh.red);
-            if (mu <= prm.mu_rel * mu0 && rdmax <= rd_tol) { result = 0; ++it; break; }
+            // weakly active bounds converge like sqrt(mu): also require that the step itself has become small
+            bool settled = true;
+            if (prm.dx_rel > 0.0 && mu <= prm.mu_rel * mu0) {
+                dxmax = block_reduce<1>(dxmax, sh.red);
+                amax = block_reduce<1>(amax, sh.red);
+                settled = ap * dxmax <= prm.dx_rel * fmax(amax, 0.01);
+            }
+            if (mu <= prm.mu_rel * mu0 && rdmax <= rd_tol && settled) { result = 0; ++it; break; }
             if (mu <= 1e-4 * prm.mu_rel * mu0) { result = (rdmax <= 1e3 * rd_tol) ? 0 : 2; ++it; break; }   // complementarity exhausted
         }
         __syncthreads();

@@ -30,7 +30,7 @@ mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
     const int n = n_pts ? n_pts[b] : n_max;
     double *slab = ws + (size_t)b * L.stride;
     __shared__ int s_flag;
-    __shared__ double s_win[hband_win_doubles(256)];      // sliding windows of the B-band recurrence (assemble_hband)
+    extern __shared__ __align__(16) double s_win[];       // sliding windows + store staging of the B-band recurrence (assemble_hband)
     if (threadIdx.x == 0) s_flag = 0;
     __syncthreads();
     if (n < N_MIN || n > n_max) {
@@ -126,7 +126,13 @@ mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
 void launch_mincurv_setup(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
                           const double *h, double w_veh, const double *w_veh_batch, double *ws, const Layout &L,
                           int32_t *status, cudaStream_t stream) {
-    mincurv_setup_kernel<<<B, 256, 0, stream>>>(n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, ws, L, status);
+    constexpr int smem = hband_win_doubles(256) * (int)sizeof(double);      // 49 KB: above the static limit
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(mincurv_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    mincurv_setup_kernel<<<B, 256, smem, stream>>>(n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, ws, L, status);
 }
 
 }  // namespace mc
