@@ -34,6 +34,13 @@ constexpr int F_TILE = 32 * LTP;   // F_I, row-major
 constexpr int BLK_TILES = LT_TILE + F_TILE;   // doubles per chain block in the slab (one contiguous bulk copy)
 constexpr unsigned BLK_BYTES = BLK_TILES * sizeof(double);
 constexpr unsigned LT_BYTES = LT_TILE * sizeof(double);
+constexpr int RING = 6;            // half-block slots (one packed LT tile or one F tile each) of the sweep ring.  Even, so that
+                                   // LT tiles only ever use even slots and F tiles odd ones: every slot has ONE consumer warp,
+                                   // which has consumed use k-1 before it waits for use k (a parity wait cannot tell use k from
+                                   // use k-2; with 5 slots the consumers alternated and warp 0 could pass a wait on a slot whose
+                                   // previous fill had not landed yet)
+constexpr int RING_PAD = RING * LT_TILE - (32 * HB_PITCH + 4 * 32 * TP);      // doubles the ring needs beyond band + tiles
+static_assert(RING_PAD > 0, "ring padding");
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -93,14 +100,15 @@ __device__ unsigned long long g_prof[24];
 
 struct PdShared {
     double band[32 * HB_PITCH];      // band rows of the current chain block (next block: prefetched in registers)
-    // The four factorisation tiles; during the triangular sweeps the same 36 KB hold the two 16.5 KB
-    // staging buffers of the TMA tile pipeline (stage s at &As[0] + s * BLK_TILES).
+    // The four factorisation tiles; during the triangular sweeps band + tiles + ringpad (49.5 KB, contiguous) hold the
+    // six 8.25 KB slots of the TMA tile ring (slot s at &band[0] + s * LT_TILE).
     double As[32 * TP];              // A'_I -> L_II, column-major: As[c * TP + r]
     double Li[32 * TP];              // Linv_I, row-major
     double Ts[32 * TP];              // T_I, row-major (upper triangular)
     double Fa[32 * TP];              // F_{I-1} -> FW_I -> F_I, row-major (updated in place)
-    uint64_t full_bar[2], empty_bar[2], aux_bar[2];
-    double xch[2][32];               // sweeps: y_I (forward) / F_I^T x_S (backward) exchanged between warps 0 and 2 per ring stage
+    double ringpad[RING_PAD];        // tail of the sweep ring
+    uint64_t full_bar[RING], empty_bar[RING], aux_bar[4];
+    double xch[4][32];               // sweeps: y_I (forward) / F_I^T x_S (backward) handed between warps 0 and 2, per visit & 3
     double vbuf[8][32];
     double red[32];
     int flag;
@@ -616,98 +624,94 @@ __device__ __forceinline__ double sm_f_mtv(const double *F, const double *v, int
 
 // ------------------------------------------------------------------------------------------------
 // solve M x = g with the stored factor.  g, x: real-indexed vectors (length n) in the slab; ypad: padded scratch.
-// The 2 nb + 1 factor blocks [0 .. nb-1, S, nb-1 .. 0] are streamed HBM -> shared by one elected thread of
-// warp 1 with cp.async.bulk (TMA, one 16.5 KB copy per block) into a two-stage ring guarded by full/empty
-// mbarriers; warp 0 runs the chain recurrences (two triangular 32x32 mat-vecs per block from shared memory),
-// warp 2 the separator-row products F_I y_I / F_I^T x_S next to it.
-// `fill` counts the ring fills of this CTA so far (parity bookkeeping); the new count is returned.
+// The factor blocks are visited in the order [0 .. nb-1, S, nb-1 .. 0]; every visit streams two tiles HBM -> shared
+// with cp.async.bulk (TMA): the packed (Linv | T) tile for warp 0, which runs the chain recurrences (two triangular
+// 32x32 mat-vecs per block), and the F tile for warp 2, which runs the separator-row products F_I y_I / F_I^T x_S
+// next to it.  The tiles go through a ring of RING = 6 slots (three blocks of prefetch: the sweeps are bound by the
+// HBM fetch latency of a tile, not by the mat-vecs) guarded by per-slot full/empty mbarriers; an elected lane of warp 1
+// is the producer.  `fill` counts the visits of this CTA so far (slot and parity bookkeeping): visit v uses fill
+// numbers 2v (LT) and 2v+1 (F), slot = fill number % RING.  The new count is returned.
 // ------------------------------------------------------------------------------------------------
 __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ tiles, const double *__restrict__ g,
                                        double *__restrict__ x, double *__restrict__ ypad, int n, int nb, unsigned fill) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int NA = n - 32;
-    double *stage0 = sh.As;
-    const unsigned nfill = 2u * nb + 1u;
+    double *ring = sh.band;
+    const unsigned nvis = 2u * nb + 1u;
     double *tb = sh.vbuf[1], *xb = sh.vbuf[0], *xs = sh.vbuf[3], *gsum = sh.vbuf[4];
-    fence_proxy_async();        // the staging area was last written through the generic proxy (factor tiles)
+    fence_proxy_async();        // the ring area was last written through the generic proxy (band rows, factor tiles)
     __syncthreads();
     if (warp == 1) {
         // ---- producer: one elected thread issues the bulk copies ----
         if (lane == 0) {
-            for (unsigned i = 0; i < nfill; ++i) {
-                const unsigned f = fill + i, st = f & 1u, k = f >> 1;
-                if (k > 0) mbar_wait_relaxed(&sh.empty_bar[st], (k - 1) & 1u);
+            for (unsigned i = 0; i < nvis; ++i) {
                 const unsigned blk = (i < (unsigned)nb) ? i : ((i == (unsigned)nb) ? (unsigned)nb : 2u * nb - i);
-                const unsigned bytes = (i == (unsigned)nb) ? LT_BYTES : BLK_BYTES;
-                mbar_expect_tx(&sh.full_bar[st], bytes);
-                tma_load_1d(stage0 + st * BLK_TILES, tiles + (size_t)blk * BLK_TILES, bytes, &sh.full_bar[st]);
+                for (unsigned h = 0; h < 2; ++h) {      // (the separator has no F tile: its slot is copied but never read)
+                    const unsigned f = 2u * (fill + i) + h, sl = f % RING, k = f / RING;
+                    if (k > 0) mbar_wait_relaxed(&sh.empty_bar[sl], (k - 1) & 1u);
+                    mbar_expect_tx(&sh.full_bar[sl], LT_BYTES);
+                    tma_load_1d(ring + sl * LT_TILE, tiles + (size_t)blk * BLK_TILES + h * LT_TILE, LT_BYTES, &sh.full_bar[sl]);
+                }
             }
         }
     } else if (warp == 2) {
-        // ---- separator-row mat-vecs, off the chain: forward gS -= F_I y_I (one block behind warp 0),
-        //      backward c_I = F_I^T x_S (ahead of warp 0).  aux_bar[st] hands y_I / c_I over per ring fill. ----
+        // ---- separator-row mat-vecs, off the chain: forward gS -= F_I y_I (behind warp 0), backward c_I = F_I^T x_S
+        //      (ahead of warp 0).  aux_bar[v & 3] / xch[v & 3] hand y_I / c_I over per visit v. ----
         double gacc = 0.0;
-        for (int I = 0; I < nb; ++I) {
-            const unsigned f = fill + I, st = f & 1u, k = f >> 1;
-            mbar_wait_relaxed(&sh.full_bar[st], k & 1u);
-            mbar_wait_relaxed(&sh.aux_bar[st], k & 1u);
-            gacc += sm_f_mv(stage0 + st * BLK_TILES + LT_TILE, sh.xch[st], lane);
+        for (unsigned i = 0; i < nvis; ++i) {
+            const unsigned v = fill + i, f = 2u * v + 1u, sl = f % RING, k = f / RING, a = v & 3u;
+            mbar_wait_relaxed(&sh.full_bar[sl], k & 1u);
+            const double *Ft = ring + sl * LT_TILE;
+            if (i < (unsigned)nb) {
+                mbar_wait_relaxed(&sh.aux_bar[a], (v >> 2) & 1u);
+                gacc += sm_f_mv(Ft, sh.xch[a], lane);
+                if (i + 1 == (unsigned)nb) {
+                    gsum[lane] = gacc;
+                    __syncwarp();
+                    named_bar_arrive(9, 64);
+                }
+            } else if (i == (unsigned)nb) {
+                mbar_wait_relaxed(&sh.aux_bar[a], (v >> 2) & 1u);          // x_S is in xs
+            } else {
+                sh.xch[a][lane] = sm_f_mtv(Ft, xs, lane);
+            }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sh.empty_bar[st]);
-        }
-        gsum[lane] = gacc;
-        __syncwarp();
-        named_bar_arrive(9, 64);
-        {
-            const unsigned f = fill + nb, st = f & 1u, k = f >> 1;
-            mbar_wait_relaxed(&sh.full_bar[st], k & 1u);
-            mbar_wait_relaxed(&sh.aux_bar[st], k & 1u);          // x_S is in xs
-            if (lane == 0) mbar_arrive(&sh.empty_bar[st]);
-        }
-        for (int i = 0; i < nb; ++i) {
-            const unsigned f = fill + nb + 1 + i, st = f & 1u, k = f >> 1;
-            mbar_wait_relaxed(&sh.full_bar[st], k & 1u);
-            sh.xch[st][lane] = sm_f_mtv(stage0 + st * BLK_TILES + LT_TILE, xs, lane);
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(&sh.aux_bar[st]); mbar_arrive(&sh.empty_bar[st]); }
+            if (lane == 0) {
+                if (i > (unsigned)nb) mbar_arrive(&sh.aux_bar[a]);
+                mbar_arrive(&sh.empty_bar[sl]);
+            }
         }
     } else {
         // ---- forward: y_I = Linv_I (g_I - T_I y_{I-1}) ----
         const long long tfw = clock64();
         double gnext = (lane < NA) ? g[lane] : 0.0;
         for (int I = 0; I < nb; ++I) {
-            const unsigned f = fill + I, st = f & 1u, k = f >> 1;
+            const unsigned v = fill + I, f = 2u * v, sl = f % RING, k = f / RING, a = v & 3u;
             const double gv = gnext;
             if (I + 1 < nb) { const int nd = 32 * (I + 1) + lane; gnext = (nd < NA) ? g[nd] : 0.0; }
             const long long tw = clock64();
-            mbar_wait(&sh.full_bar[st], k & 1u);
+            mbar_wait(&sh.full_bar[sl], k & 1u);
             PROF_ADD(7, tw);
-            const long long t1 = clock64();
-            const double *LT = stage0 + st * BLK_TILES;
-            double v = gv;
-            if (I > 0) v -= sm_t_mv(LT, sh.xch[st ^ 1u], lane);
-            tb[lane] = v;
+            const double *LT = ring + sl * LT_TILE;
+            double vv = gv;
+            if (I > 0) vv -= sm_t_mv(LT, sh.xch[(v - 1u) & 3u], lane);
+            tb[lane] = vv;
             __syncwarp();
-            PROF_ADD(16, t1);
-            const long long t2 = clock64();
             const double y = sm_linv_mv(LT, tb, lane);
-            sh.xch[st][lane] = y;
-            PROF_ADD(17, t2);
-            const long long t3 = clock64();
+            sh.xch[a][lane] = y;
             ypad[32 * I + lane] = y;
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&sh.aux_bar[st]); mbar_arrive(&sh.empty_bar[st]); }
-            PROF_ADD(18, t3);
+            if (lane == 0) { mbar_arrive(&sh.aux_bar[a]); mbar_arrive(&sh.empty_bar[sl]); }
         }
         PROF_ADD(21, tfw);
         const long long tsep = clock64();
         // ---- separator: x_S = LinvS^T LinvS (g_S - sum F_I y_I) ----
         {
-            const unsigned f = fill + nb, st = f & 1u, k = f >> 1;
+            const unsigned v = fill + nb, f = 2u * v, sl = f % RING, k = f / RING, a = v & 3u;
             const double gs0 = g[NA + lane];
-            mbar_wait(&sh.full_bar[st], k & 1u);
+            mbar_wait(&sh.full_bar[sl], k & 1u);
             named_bar_sync(9, 64);
-            const double *LS = stage0 + st * BLK_TILES;
+            const double *LS = ring + sl * LT_TILE;
             tb[lane] = gs0 - gsum[lane];
             __syncwarp();
             const double ys = sm_linv_mv(LS, tb, lane);
@@ -717,7 +721,7 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
             xs[lane] = xv;
             x[NA + lane] = xv;
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&sh.aux_bar[st]); mbar_arrive(&sh.empty_bar[st]); }
+            if (lane == 0) { mbar_arrive(&sh.aux_bar[a]); mbar_arrive(&sh.empty_bar[sl]); }
         }
         PROF_ADD(22, tsep);
         const long long tbw = clock64();
@@ -726,15 +730,15 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
         double ynext = ypad[32 * (nb - 1) + lane];
         for (int i = 0; i < nb; ++i) {
             const int I = nb - 1 - i;
-            const unsigned f = fill + nb + 1 + i, st = f & 1u, k = f >> 1;
+            const unsigned v = fill + nb + 1 + i, f = 2u * v, sl = f % RING, k = f / RING, a = v & 3u;
             const double yv = ynext;
             if (I > 0) ynext = ypad[32 * (I - 1) + lane];
             const long long tw = clock64();
-            mbar_wait(&sh.full_bar[st], k & 1u);
-            mbar_wait(&sh.aux_bar[st], k & 1u);
+            mbar_wait(&sh.full_bar[sl], k & 1u);
+            mbar_wait(&sh.aux_bar[a], (v >> 2) & 1u);
             PROF_ADD(19, tw);
-            const double *LT = stage0 + st * BLK_TILES;
-            tb[lane] = yv - sh.xch[st][lane] - u;
+            const double *LT = ring + sl * LT_TILE;
+            tb[lane] = yv - sh.xch[a][lane] - u;
             __syncwarp();
             const double xv = sm_linv_mtv(LT, tb, lane);
             xb[lane] = xv;
@@ -742,14 +746,14 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
             __syncwarp();
             u = (I > 0) ? sm_t_mtv(LT, xb, lane) : 0.0;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sh.empty_bar[st]);
+            if (lane == 0) mbar_arrive(&sh.empty_bar[sl]);
         }
         PROF_ADD(20, tbw);
     }
     const long long tend = clock64();
     __syncthreads();
     PROF_ADD(23, tend);
-    return fill + nfill;
+    return fill + nvis;
 }
 
 // banded cyclic mat-vec out = H v (real-indexed)
@@ -778,9 +782,8 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PdShared &sh = *reinterpret_cast<PdShared *>(smem_raw);
     if (threadIdx.x == 0) {
-        mbar_init(&sh.full_bar[0], 1); mbar_init(&sh.full_bar[1], 1);
-        mbar_init(&sh.empty_bar[0], 2); mbar_init(&sh.empty_bar[1], 2);
-        mbar_init(&sh.aux_bar[0], 1); mbar_init(&sh.aux_bar[1], 1);
+        for (int i = 0; i < RING; ++i) { mbar_init(&sh.full_bar[i], 1); mbar_init(&sh.empty_bar[i], 1); }
+        for (int i = 0; i < 4; ++i) mbar_init(&sh.aux_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -1001,9 +1004,8 @@ mincurv_pdip_kappa_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, d
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PdShared &sh = *reinterpret_cast<PdShared *>(smem_raw);
     if (threadIdx.x == 0) {
-        mbar_init(&sh.full_bar[0], 1); mbar_init(&sh.full_bar[1], 1);
-        mbar_init(&sh.empty_bar[0], 2); mbar_init(&sh.empty_bar[1], 2);
-        mbar_init(&sh.aux_bar[0], 1); mbar_init(&sh.aux_bar[1], 1);
+        for (int i = 0; i < RING; ++i) { mbar_init(&sh.full_bar[i], 1); mbar_init(&sh.empty_bar[i], 1); }
+        for (int i = 0; i < 4; ++i) mbar_init(&sh.aux_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
