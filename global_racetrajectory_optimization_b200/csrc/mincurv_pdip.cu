@@ -856,14 +856,25 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
 
         // Vector phases: the reciprocals 1/s_u, 1/s_l are state (ISU, ISL), so one interior-point iteration
         // costs four divisions per variable; step lengths come from max-ratios (no division per element).
+        // Every thread owns the elements i = tid + k * 96; the loops take them in groups of VG with all loads of a
+        // group issued before the first use (the vectors live in L2/HBM: one element at a time, each of the ~10
+        // trips of a loop paid the full memory latency, ~9 % of the kernel).
+        constexpr int VG = 4, VS = VG * PD_THREADS;
         for (it = 0; it < prm.max_iter; ++it) {
             // ---- barrier diagonal and affine right-hand side ----
-#pragma unroll 2
-    #pragma unroll 1
-        for (int i = threadIdx.x; i < n; i += PD_THREADS) {
-                const double lu = LU[i], ll = LL[i];
-                DD[i] = lu * ISU[i] + ll * ISL[i];
-                RHS[i] = -RD[i] + lu - ll;
+#pragma unroll 1
+            for (int i0 = threadIdx.x; i0 < n; i0 += VS) {
+                double lu[VG], ll[VG], isu[VG], isl[VG], rd[VG];
+#pragma unroll
+                for (int k = 0; k < VG; ++k) {
+                    const int i = min(i0 + k * PD_THREADS, n - 1);
+                    lu[k] = LU[i]; ll[k] = LL[i]; isu[k] = ISU[i]; isl[k] = ISL[i]; rd[k] = RD[i];
+                }
+#pragma unroll
+                for (int k = 0; k < VG; ++k) {
+                    const int i = i0 + k * PD_THREADS;
+                    if (i < n) { DD[i] = lu[k] * isu[k] + ll[k] * isl[k]; RHS[i] = -rd[k] + lu[k] - ll[k]; }
+                }
             }
             __syncthreads();
             const long long tf0 = clock64();
@@ -874,18 +885,27 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             PROF_ADD(6, ts0);
             // ---- affine direction: step lengths 1 / max-ratio; mu_aff as a polynomial in (ap, ad) ----
             double rp = 0.0, rdl = 0.0, c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
-#pragma unroll 2
-    #pragma unroll 1
-        for (int i = threadIdx.x; i < n; i += PD_THREADS) {
-                const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i];
-                const double p = dx * ISU[i], m = dx * ISL[i];
-                rp = fmax(rp, fmax(p, -m));                 // s_u - a dx >= 0, s_l + a dx >= 0
-                rdl = fmax(rdl, fmax(1.0 - p, 1.0 + m));    // dlu / lu = -1 + p, dll / ll = -1 - m
-                const double dlu = lu * (p - 1.0), dll = -ll * (1.0 + m);
-                c00 += su * lu + sl * ll;
-                c01 += su * dlu + sl * dll;                 // coefficient of ad
-                c10 += dx * (ll - lu);                      // coefficient of ap
-                c11 += dx * (dll - dlu);                    // coefficient of ap * ad
+#pragma unroll 1
+            for (int i0 = threadIdx.x; i0 < n; i0 += VS) {
+                double su[VG], sl[VG], lu[VG], ll[VG], dx[VG], isu[VG], isl[VG];
+#pragma unroll
+                for (int k = 0; k < VG; ++k) {
+                    const int i = min(i0 + k * PD_THREADS, n - 1);
+                    su[k] = SU[i]; sl[k] = SL[i]; lu[k] = LU[i]; ll[k] = LL[i]; dx[k] = DX[i]; isu[k] = ISU[i]; isl[k] = ISL[i];
+                }
+#pragma unroll
+                for (int k = 0; k < VG; ++k) {
+                    if (i0 + k * PD_THREADS < n) {
+                        const double p = dx[k] * isu[k], m = dx[k] * isl[k];
+                        rp = fmax(rp, fmax(p, -m));                 // s_u - a dx >= 0, s_l + a dx >= 0
+                        rdl = fmax(rdl, fmax(1.0 - p, 1.0 + m));    // dlu / lu = -1 + p, dll / ll = -1 - m
+                        const double dlu = lu[k] * (p - 1.0), dll = -ll[k] * (1.0 + m);
+                        c00 += su[k] * lu[k] + sl[k] * ll[k];
+                        c01 += su[k] * dlu + sl[k] * dll;           // coefficient of ad
+                        c10 += dx[k] * (ll[k] - lu[k]);             // coefficient of ap
+                        c11 += dx[k] * (dll - dlu);                 // coefficient of ap * ad
+                    }
+                }
             }
             rp = block_reduce<1>(rp, sh.red);
             rdl = block_reduce<1>(rdl, sh.red);
@@ -897,49 +917,80 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             sigma = sigma * sigma * sigma;
             const double smu = sigma * mu;
             // ---- corrector right-hand side ----
-#pragma unroll 2
-    #pragma unroll 1
-        for (int i = threadIdx.x; i < n; i += PD_THREADS) {
-                const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i], isu = ISU[i], isl = ISL[i];
-                const double dlu = lu * (dx * isu - 1.0), dll = -ll * (1.0 + dx * isl);
-                const double tu = smu - su * lu + dx * dlu;
-                const double tl = smu - sl * ll - dx * dll;
-                TU[i] = tu; TL[i] = tl;
-                RHS[i] = -RD[i] - tu * isu + tl * isl;
+#pragma unroll 1
+            for (int i0 = threadIdx.x; i0 < n; i0 += VS) {
+                double su[VG], sl[VG], lu[VG], ll[VG], dx[VG], isu[VG], isl[VG], rd[VG];
+#pragma unroll
+                for (int k = 0; k < VG; ++k) {
+                    const int i = min(i0 + k * PD_THREADS, n - 1);
+                    su[k] = SU[i]; sl[k] = SL[i]; lu[k] = LU[i]; ll[k] = LL[i]; dx[k] = DX[i]; isu[k] = ISU[i]; isl[k] = ISL[i]; rd[k] = RD[i];
+                }
+#pragma unroll
+                for (int k = 0; k < VG; ++k) {
+                    const int i = i0 + k * PD_THREADS;
+                    if (i < n) {
+                        const double dlu = lu[k] * (dx[k] * isu[k] - 1.0), dll = -ll[k] * (1.0 + dx[k] * isl[k]);
+                        const double tu = smu - su[k] * lu[k] + dx[k] * dlu;
+                        const double tl = smu - sl[k] * ll[k] - dx[k] * dll;
+                        TU[i] = tu; TL[i] = tl;
+                        RHS[i] = -rd[k] - tu * isu[k] + tl * isl[k];
+                    }
+                }
             }
             __syncthreads();
             const long long ts1 = clock64();
             fill = solve(sh, tiles, RHS, DX, YP, n, nb, fill);
             PROF_ADD(6, ts1);
             rp = 0.0; rdl = 0.0;
-#pragma unroll 2
-    #pragma unroll 1
-        for (int i = threadIdx.x; i < n; i += PD_THREADS) {
-                const double lu = LU[i], ll = LL[i], dx = DX[i], isu = ISU[i], isl = ISL[i];
-                const double dlu = (TU[i] + lu * dx) * isu, dll = (TL[i] - ll * dx) * isl;
-                rp = fmax(rp, fmax(dx * isu, -dx * isl));
-                rdl = fmax(rdl, fmax(-dlu / lu, -dll / ll));
+#pragma unroll 1
+            for (int i0 = threadIdx.x; i0 < n; i0 += VS) {
+                double lu[VG], ll[VG], dx[VG], isu[VG], isl[VG], tu[VG], tl[VG];
+#pragma unroll
+                for (int k = 0; k < VG; ++k) {
+                    const int i = min(i0 + k * PD_THREADS, n - 1);
+                    lu[k] = LU[i]; ll[k] = LL[i]; dx[k] = DX[i]; isu[k] = ISU[i]; isl[k] = ISL[i]; tu[k] = TU[i]; tl[k] = TL[i];
+                }
+#pragma unroll
+                for (int k = 0; k < VG; ++k) {
+                    if (i0 + k * PD_THREADS < n) {
+                        const double dlu = (tu[k] + lu[k] * dx[k]) * isu[k], dll = (tl[k] - ll[k] * dx[k]) * isl[k];
+                        rp = fmax(rp, fmax(dx[k] * isu[k], -dx[k] * isl[k]));
+                        rdl = fmax(rdl, fmax(-dlu / lu[k], -dll / ll[k]));
+                    }
+                }
             }
             rp = block_reduce<1>(rp, sh.red);
             rdl = block_reduce<1>(rdl, sh.red);
             ap = (prm.eta < rp) ? prm.eta / rp : 1.0;       // min(1, eta / max-ratio)
             ad = (prm.eta < rdl) ? prm.eta / rdl : 1.0;
             double musum2 = 0.0, rdmax = 0.0, dxmax = 0.0, amax = 0.0;
-#pragma unroll 2
-    #pragma unroll 1
-        for (int i = threadIdx.x; i < n; i += PD_THREADS) {
-                const double su = SU[i], sl = SL[i], lu = LU[i], ll = LL[i], dx = DX[i];
-                const double dlu = (TU[i] + lu * dx) * ISU[i], dll = (TL[i] - ll * dx) * ISL[i];
-                const double an = AL[i] + ap * dx, lun = lu + ad * dlu, lln = ll + ad * dll;
-                const double sun = su - ap * dx, sln = sl + ap * dx;
-                // H dx = rhs - D dx  (M dx = rhs)
-                const double rdn = RD[i] + ap * (RHS[i] - DD[i] * dx) + ad * (dlu - dll);
-                AL[i] = an; LU[i] = lun; LL[i] = lln; RD[i] = rdn; SU[i] = sun; SL[i] = sln;
-                ISU[i] = 1.0 / sun; ISL[i] = 1.0 / sln;
-                musum2 += sun * lun + sln * lln;
-                rdmax = fmax(rdmax, fabs(rdn));
-                dxmax = fmax(dxmax, fabs(dx));
-                amax = fmax(amax, fabs(an));
+            constexpr int VG2 = 2, VS2 = VG2 * PD_THREADS;        // 13 input vectors: groups of two
+#pragma unroll 1
+            for (int i0 = threadIdx.x; i0 < n; i0 += VS2) {
+                double su[VG2], sl[VG2], lu[VG2], ll[VG2], dx[VG2], isu[VG2], isl[VG2], tu[VG2], tl[VG2], al[VG2], rd[VG2], rh[VG2], dd[VG2];
+#pragma unroll
+                for (int k = 0; k < VG2; ++k) {
+                    const int i = min(i0 + k * PD_THREADS, n - 1);
+                    su[k] = SU[i]; sl[k] = SL[i]; lu[k] = LU[i]; ll[k] = LL[i]; dx[k] = DX[i]; isu[k] = ISU[i]; isl[k] = ISL[i];
+                    tu[k] = TU[i]; tl[k] = TL[i]; al[k] = AL[i]; rd[k] = RD[i]; rh[k] = RHS[i]; dd[k] = DD[i];
+                }
+#pragma unroll
+                for (int k = 0; k < VG2; ++k) {
+                    const int i = i0 + k * PD_THREADS;
+                    if (i < n) {
+                        const double dlu = (tu[k] + lu[k] * dx[k]) * isu[k], dll = (tl[k] - ll[k] * dx[k]) * isl[k];
+                        const double an = al[k] + ap * dx[k], lun = lu[k] + ad * dlu, lln = ll[k] + ad * dll;
+                        const double sun = su[k] - ap * dx[k], sln = sl[k] + ap * dx[k];
+                        // H dx = rhs - D dx  (M dx = rhs)
+                        const double rdn = rd[k] + ap * (rh[k] - dd[k] * dx[k]) + ad * (dlu - dll);
+                        AL[i] = an; LU[i] = lun; LL[i] = lln; RD[i] = rdn; SU[i] = sun; SL[i] = sln;
+                        ISU[i] = 1.0 / sun; ISL[i] = 1.0 / sln;
+                        musum2 += sun * lun + sln * lln;
+                        rdmax = fmax(rdmax, fabs(rdn));
+                        dxmax = fmax(dxmax, fabs(dx[k]));
+                        amax = fmax(amax, fabs(an));
+                    }
+                }
             }
             mu = block_reduce<0>(musum2, sh.red) / (2.0 * n);
             rdmax = block_reduce<1>(rdmax, sh.red);
