@@ -77,9 +77,17 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, unsigned parity
         __nanosleep(32);
     }
 }
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+// The factor tiles are a stream (written once, read four times per iteration, ~0.5 MB per instance, far beyond what L2
+// can keep for 592 resident instances): copies and stores of tiles and band rows carry an evict-first L2 policy so that
+// they do not push the O(N) iterate vectors of the interior-point loop out of L2.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -307,8 +315,8 @@ __device__ __forceinline__ void rowblock_times_linvT(double *X, const double *Li
             for (int s = 0; s < 2; ++s) dmma(c2, a[2 * K + s], Li[(8 * j + g) * TP + 8 * K + 4 * s + q]);
         const int r = 8 * rb + g, c = 8 * j + 2 * q;
         *reinterpret_cast<double2 *>(&X[r * TP + c]) = make_double2(c2[0], c2[1]);
-        gx[r * LTP + c] = c2[0];
-        gx[r * LTP + c + 1] = c2[1];
+        __stcs(&gx[r * LTP + c], c2[0]);
+        __stcs(&gx[r * LTP + c + 1], c2[1]);
     }
 }
 
@@ -322,15 +330,11 @@ __device__ __noinline__ bool factor_chain(PdShared &sh, double *__restrict__ til
     __syncthreads();                      // the fill warps have assembled A'_0 into As
     for (int I = 0; I <= nb; ++I) {
         // =========================== phase A ===========================
-        const long long tA = clock64();
         if (I == nb) named_bar_sync(3, PD_THREADS);      // the fill warps have put the separator Schur complement into As
         const long long tB = clock64();
         ok = chol_inv32(sh.As, sh.Li, lane) && ok;
         const long long tC = clock64();
-        if (blockIdx.x == 0 && lane == 0) {
-            atomicAdd(&g_prof[0], (unsigned long long)(tB - tA));
-            atomicAdd(&g_prof[1], (unsigned long long)(tC - tB));
-        }
+        if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_prof[1], (unsigned long long)(tC - tB));
         __syncthreads();
         const long long tE = clock64();
         PROF_ADD(3, tC);
@@ -340,7 +344,7 @@ __device__ __noinline__ bool factor_chain(PdShared &sh, double *__restrict__ til
             double *gt = tiles + (size_t)I * BLK_TILES;
 #pragma unroll 4
             for (int r = 0; r < 32; ++r)
-                if (lane <= r) gt[r * LTP + lane] = sh.Li[r * TP + lane];
+                if (lane <= r) __stcs(&gt[r * LTP + lane], sh.Li[r * TP + lane]);
             if (I < nb) {
                 // ---- F_I = FW_I Linv_I^T, in place in the shared F tile and to HBM ----
                 double *gf = gt + LT_TILE;
@@ -403,8 +407,8 @@ __device__ __forceinline__ void coupling_rowblock(PdShared &sh, double *__restri
             }
         const int r = 8 * i + g, c = 8 * j + 2 * q;
         *reinterpret_cast<double2 *>(&sh.Ts[r * TP + c]) = make_double2(c2[0], c2[1]);
-        if (c >= r) gn[r * LTP + c + 1] = c2[0];
-        if (c + 1 >= r) gn[r * LTP + c + 2] = c2[1];
+        if (c >= r) __stcs(&gn[r * LTP + c + 1], c2[0]);
+        if (c + 1 >= r) __stcs(&gn[r * LTP + c + 2], c2[1]);
     }
 }
 
@@ -433,7 +437,7 @@ __device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict_
     if (1 < nb) {
         const double *src = HB + (size_t)32 * HB_PITCH + (warp - 1) * 544;
 #pragma unroll
-        for (int t = 0; t < 17; ++t) breg[t] = src[32 * t + lane];
+        for (int t = 0; t < 17; ++t) breg[t] = __ldcs(&src[32 * t + lane]);
         const int nd = 32 + 16 * (warp - 1) + lane;
         dreg = (lane < 16 && nd < NA) ? DD[nd] : 0.0;
     }
@@ -509,7 +513,7 @@ __device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict_
             if (I + 2 < nb) {
                 const double *src = HB + (size_t)(base + 64) * HB_PITCH + (warp - 1) * 544;
 #pragma unroll
-                for (int t = 0; t < 17; ++t) breg[t] = src[32 * t + lane];
+                for (int t = 0; t < 17; ++t) breg[t] = __ldcs(&src[32 * t + lane]);
                 const int nd = base + 64 + 16 * (warp - 1) + lane;
                 dreg = (lane < 16 && nd < NA) ? DD[nd] : 0.0;
             }
@@ -644,13 +648,14 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
     if (warp == 1) {
         // ---- producer: one elected thread issues the bulk copies ----
         if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
             for (unsigned i = 0; i < nvis; ++i) {
                 const unsigned blk = (i < (unsigned)nb) ? i : ((i == (unsigned)nb) ? (unsigned)nb : 2u * nb - i);
                 for (unsigned h = 0; h < 2; ++h) {      // (the separator has no F tile: its slot is copied but never read)
                     const unsigned f = 2u * (fill + i) + h, sl = f % RING, k = f / RING;
                     if (k > 0) mbar_wait_relaxed(&sh.empty_bar[sl], (k - 1) & 1u);
                     mbar_expect_tx(&sh.full_bar[sl], LT_BYTES);
-                    tma_load_1d(ring + sl * LT_TILE, tiles + (size_t)blk * BLK_TILES + h * LT_TILE, LT_BYTES, &sh.full_bar[sl]);
+                    tma_load_1d(ring + sl * LT_TILE, tiles + (size_t)blk * BLK_TILES + h * LT_TILE, LT_BYTES, &sh.full_bar[sl], pol);
                 }
             }
         }
@@ -862,6 +867,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
         constexpr int VG = 4, VS = VG * PD_THREADS;
         for (it = 0; it < prm.max_iter; ++it) {
             // ---- barrier diagonal and affine right-hand side ----
+            const long long tv1 = clock64();
 #pragma unroll 1
             for (int i0 = threadIdx.x; i0 < n; i0 += VS) {
                 double lu[VG], ll[VG], isu[VG], isl[VG], rd[VG];
@@ -877,6 +883,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
                 }
             }
             __syncthreads();
+            PROF_ADD(16, tv1);
             const long long tf0 = clock64();
             if (!factor(sh, HB, DD, tiles, n, nb)) { result = 3; break; }
             PROF_ADD(10, tf0);
@@ -884,6 +891,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             fill = solve(sh, tiles, RHS, DX, YP, n, nb, fill);
             PROF_ADD(6, ts0);
             // ---- affine direction: step lengths 1 / max-ratio; mu_aff as a polynomial in (ap, ad) ----
+            const long long tv2 = clock64();
             double rp = 0.0, rdl = 0.0, c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
 #pragma unroll 1
             for (int i0 = threadIdx.x; i0 < n; i0 += VS) {
@@ -916,6 +924,8 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             double sigma = mua / mu;
             sigma = sigma * sigma * sigma;
             const double smu = sigma * mu;
+            PROF_ADD(17, tv2);
+            const long long tv3 = clock64();
             // ---- corrector right-hand side ----
 #pragma unroll 1
             for (int i0 = threadIdx.x; i0 < n; i0 += VS) {
@@ -938,9 +948,11 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
                 }
             }
             __syncthreads();
+            PROF_ADD(18, tv3);
             const long long ts1 = clock64();
             fill = solve(sh, tiles, RHS, DX, YP, n, nb, fill);
             PROF_ADD(6, ts1);
+            const long long tv4 = clock64();
             rp = 0.0; rdl = 0.0;
 #pragma unroll 1
             for (int i0 = threadIdx.x; i0 < n; i0 += VS) {
@@ -963,6 +975,8 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             rdl = block_reduce<1>(rdl, sh.red);
             ap = (prm.eta < rp) ? prm.eta / rp : 1.0;       // min(1, eta / max-ratio)
             ad = (prm.eta < rdl) ? prm.eta / rdl : 1.0;
+            PROF_ADD(15, tv4);
+            const long long tv5 = clock64();
             double musum2 = 0.0, rdmax = 0.0, dxmax = 0.0, amax = 0.0;
             constexpr int VG2 = 2, VS2 = VG2 * PD_THREADS;        // 13 input vectors: groups of two
 #pragma unroll 1
@@ -994,6 +1008,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             }
             mu = block_reduce<0>(musum2, sh.red) / (2.0 * n);
             rdmax = block_reduce<1>(rdmax, sh.red);
+            PROF_ADD(0, tv5);
             // weakly active bounds converge like sqrt(mu): also require that the step itself has become small
             bool settled = true;
             if (prm.dx_rel > 0.0 && mu <= prm.mu_rel * mu0) {
