@@ -239,7 +239,13 @@ def run_b200(args) -> dict:
                      "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                      "kernel_ms": pdip_last, "setup_kernel_ms": setup_last,
                      "algorithmic_bytes_per_launch": alg_bytes,
-                     "note": "algorithmic bytes = 40 B/point (SURVEY 8d); the kernel is fp64-FMA/latency bound, see DESIGN.md"},
+                     # implementation traffic (ncu dram bytes per QP x QPs of this launch) over the live kernel time
+                     "traffic_gbs": (traffic / (pdip_last * 1e-3) / 1e9) if traffic else None,
+                     "traffic_frac_of_peak": (traffic / (pdip_last * 1e-3) / 1e9 / hbm_peak) if traffic else None,
+                     "note": "algorithmic bytes = 40 B/point (SURVEY 8d). The kernel re-streams its block-Cholesky factor "
+                             "(written once, read four times per interior-point iteration): traffic >> algorithmic bytes by "
+                             "construction; it is bound by the serial pivot/sweep chain of one warp per instance and by that "
+                             "implementation traffic, see DESIGN.md section 5"},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(n, sample=1)
