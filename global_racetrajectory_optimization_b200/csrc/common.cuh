@@ -63,24 +63,39 @@ __device__ __forceinline__ double block_reduce(double v, double *red) {
 // Block-cooperative; all arrays may live in global or shared memory; callers __syncthreads() after.
 // ---------------------------------------------------------------------------------------------
 // forward pivots dfw_i = diag_i - off_{i-1}^2 / dfw_{i-1}, backward pivots dbw_i = diag_i - off_i^2 / dbw_{i+1}
+// Each chunk recurrence is split into its warm-up (no stores: unrolled, so that the loads of eight steps are in
+// flight together -- rolled, every step paid one memory round trip and these loops were ~45 % of the assembly
+// kernel) and the TRI_CHUNK steps that store.
 __device__ inline void tri_pivots(const double *diag, const double *off, double *dfw, double *dbw, int n) {
     for (int c0 = threadIdx.x * TRI_CHUNK; c0 < n; c0 += blockDim.x * TRI_CHUNK) {
         const int c1 = min(c0 + TRI_CHUNK, n);
         int i = wrapi(c0 - TRI_WARM, n);
         double prev = diag[i];
-        for (int s = c0 - TRI_WARM + 1; s < c1; ++s) {
+#pragma unroll 8
+        for (int s = 0; s < TRI_WARM - 1; ++s) {
             const double o = off[i];
             i = (i + 1 == n) ? 0 : i + 1;
             prev = diag[i] - o * o / prev;
-            if (s >= c0) dfw[i] = prev;
+        }
+        for (int s = c0; s < c1; ++s) {
+            const double o = off[i];
+            i = (i + 1 == n) ? 0 : i + 1;
+            prev = diag[i] - o * o / prev;
+            dfw[i] = prev;
         }
         i = wrapi(c1 - 1 + TRI_WARM, n);
         double nxt = diag[i];
-        for (int s = c1 - 2 + TRI_WARM; s >= c0; --s) {
+#pragma unroll 8
+        for (int s = 0; s < TRI_WARM - 1; ++s) {
             i = (i == 0) ? n - 1 : i - 1;
             const double o = off[i];
             nxt = diag[i] - o * o / nxt;
-            if (s < c1) dbw[i] = nxt;
+        }
+        for (int s = c1 - 1; s >= c0; --s) {
+            i = (i == 0) ? n - 1 : i - 1;
+            const double o = off[i];
+            nxt = diag[i] - o * o / nxt;
+            dbw[i] = nxt;
         }
     }
 }
@@ -94,11 +109,18 @@ __device__ inline void tri_solve2(const double *lfw, const double *invd, const d
         const int c1 = min(c0 + TRI_CHUNK, n);
         int i = wrapi(c0 - TRI_WARM, n);
         double px = 0.0, py = 0.0;
-        for (int s = c0 - TRI_WARM; s < c1; ++s) {
+#pragma unroll 8
+        for (int s = 0; s < TRI_WARM; ++s) {
             const double l = lfw[i];
             px = rx[i] - l * px;
             py = ry[i] - l * py;
-            if (s >= c0) { yx[i] = px; yy[i] = py; }
+            i = (i + 1 == n) ? 0 : i + 1;
+        }
+        for (int s = c0; s < c1; ++s) {
+            const double l = lfw[i];
+            px = rx[i] - l * px;
+            py = ry[i] - l * py;
+            yx[i] = px; yy[i] = py;
             i = (i + 1 == n) ? 0 : i + 1;
         }
     }
@@ -107,11 +129,18 @@ __device__ inline void tri_solve2(const double *lfw, const double *invd, const d
         const int c1 = min(c0 + TRI_CHUNK, n);
         int i = wrapi(c1 - 1 + TRI_WARM, n);
         double nx = 0.0, ny = 0.0;
-        for (int s = c1 - 1 + TRI_WARM; s >= c0; --s) {
+#pragma unroll 8
+        for (int s = 0; s < TRI_WARM; ++s) {
             const double o = off[i], id = invd[i];
             nx = (yx[i] - o * nx) * id;
             ny = (yy[i] - o * ny) * id;
-            if (s < c1) { mx[i] = nx; my[i] = ny; }
+            i = (i == 0) ? n - 1 : i - 1;
+        }
+        for (int s = c1 - 1; s >= c0; --s) {
+            const double o = off[i], id = invd[i];
+            nx = (yx[i] - o * nx) * id;
+            ny = (yy[i] - o * ny) * id;
+            mx[i] = nx; my[i] = ny;
             i = (i == 0) ? n - 1 : i - 1;
         }
     }

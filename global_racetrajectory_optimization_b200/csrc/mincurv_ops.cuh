@@ -26,22 +26,38 @@ __device__ inline void assemble_hband(double *slab, const Layout &L, int n, cons
         const int c1 = min(c0 + TRI_CHUNK, n);
         int i = wrapi(c0 - TRI_WARM, n);
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, rprev = 0.0;       // V_c = w_c + rho-_{c-1}^2 V_{c-1}
-        for (int s = c0 - TRI_WARM; s < c1; ++s) {
+#pragma unroll 8
+        for (int s = 0; s < TRI_WARM; ++s) {                     // warm-up: no stores, loads of eight steps in flight
             const double ww = wk ? 1.0 + wk[i] : 1.0;
             const double sx = SX[i], sy = ww * SY[i], r2 = rprev * rprev;
             a0 = fma(r2, a0, sy * SY[i]); a1 = fma(r2, a1, sx * sy); a2 = fma(r2, a2, ww * sx * sx);
-            if (s >= c0) { V0[i] = a0; V1[i] = a1; V2[i] = a2; }
+            rprev = RHOM[i];
+            i = (i + 1 == n) ? 0 : i + 1;
+        }
+        for (int s = c0; s < c1; ++s) {
+            const double ww = wk ? 1.0 + wk[i] : 1.0;
+            const double sx = SX[i], sy = ww * SY[i], r2 = rprev * rprev;
+            a0 = fma(r2, a0, sy * SY[i]); a1 = fma(r2, a1, sx * sy); a2 = fma(r2, a2, ww * sx * sx);
+            V0[i] = a0; V1[i] = a1; V2[i] = a2;
             rprev = RHOM[i];
             i = (i + 1 == n) ? 0 : i + 1;
         }
         i = wrapi(c1 - 1 + TRI_WARM, n);
         a0 = a1 = a2 = 0.0;
         double rnext = 0.0;                                        // U_c = w_c + rho+_{c+1}^2 U_{c+1}
-        for (int s = c1 - 1 + TRI_WARM; s >= c0; --s) {
+#pragma unroll 8
+        for (int s = 0; s < TRI_WARM; ++s) {
             const double ww = wk ? 1.0 + wk[i] : 1.0;
             const double sx = SX[i], sy = ww * SY[i], r2 = rnext * rnext;
             a0 = fma(r2, a0, sy * SY[i]); a1 = fma(r2, a1, sx * sy); a2 = fma(r2, a2, ww * sx * sx);
-            if (s < c1) { U0[i] = a0; U1[i] = a1; U2[i] = a2; }
+            rnext = RHOP[i];
+            i = (i == 0) ? n - 1 : i - 1;
+        }
+        for (int s = c1 - 1; s >= c0; --s) {
+            const double ww = wk ? 1.0 + wk[i] : 1.0;
+            const double sx = SX[i], sy = ww * SY[i], r2 = rnext * rnext;
+            a0 = fma(r2, a0, sy * SY[i]); a1 = fma(r2, a1, sx * sy); a2 = fma(r2, a2, ww * sx * sx);
+            U0[i] = a0; U1[i] = a1; U2[i] = a2;
             rnext = RHOP[i];
             i = (i == 0) ? n - 1 : i - 1;
         }

@@ -299,6 +299,11 @@ __device__ __forceinline__ void s_update(double (&sacc)[2][4][2], const double *
 }
 
 
+// CTA-wide barrier between the warp roles of the factorisation.  The roles sit in different (noinline) functions, so the
+// barrier is reached at different program points: a named barrier with an explicit thread count states exactly that
+// (every warp arrives convergently; __syncthreads() in role-divergent code is flagged by compute-sanitizer synccheck).
+__device__ __forceinline__ void role_sync() { named_bar_sync(10, PD_THREADS); }
+
 // ---- one 8-row block of  X Linv^T  (Linv lower triangular: k blocks K <= j), in place in the shared tile X and
 //      to the HBM tile gx (pitch LTP).  Used for F_I = FW_I Linv_I^T. ----
 __device__ __forceinline__ void rowblock_times_linvT(double *X, const double *Li, double *__restrict__ gx, int rb, int g, int q) {
@@ -327,7 +332,7 @@ __device__ __noinline__ bool factor_chain(PdShared &sh, double *__restrict__ til
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
     bool ok = true;
-    __syncthreads();                      // the fill warps have assembled A'_0 into As
+    role_sync();                      // the fill warps have assembled A'_0 into As
     for (int I = 0; I <= nb; ++I) {
         // =========================== phase A ===========================
         if (I == nb) named_bar_sync(3, PD_THREADS);      // the fill warps have put the separator Schur complement into As
@@ -335,7 +340,7 @@ __device__ __noinline__ bool factor_chain(PdShared &sh, double *__restrict__ til
         ok = chol_inv32(sh.As, sh.Li, lane) && ok;
         const long long tC = clock64();
         if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_prof[1], (unsigned long long)(tC - tB));
-        __syncthreads();
+        role_sync();
         const long long tE = clock64();
         PROF_ADD(3, tC);
         // =========================== phase B ===========================
@@ -354,7 +359,7 @@ __device__ __noinline__ bool factor_chain(PdShared &sh, double *__restrict__ til
         }
         const long long tS2 = clock64();
         PROF_ADD(4, tE);
-        __syncthreads();
+        role_sync();
         PROF_ADD(5, tS2);
     }
     return ok;
@@ -441,7 +446,7 @@ __device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict_
         const int nd = 32 + 16 * (warp - 1) + lane;
         dreg = (lane < 16 && nd < NA) ? DD[nd] : 0.0;
     }
-    __syncthreads();
+    role_sync();
     for (int I = 0; I <= nb; ++I) {
         const int base = 32 * I;
         // =========================== phase A ===========================
@@ -497,7 +502,7 @@ __device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict_
                 }
             }
         }
-        __syncthreads();
+        role_sync();
         // =========================== phase B ===========================
         if (I + 1 < nb) {
             // ---- T_{I+1} = B_I Linv_I^T (band rows of block I, coupling part) ----
@@ -521,7 +526,7 @@ __device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict_
             if (warp == 1) { assemble_rowblock<0>(sh, base + 32, NA, true, g, q); assemble_rowblock<1>(sh, base + 32, NA, true, g, q); }
             else           { assemble_rowblock<2>(sh, base + 32, NA, true, g, q); assemble_rowblock<3>(sh, base + 32, NA, true, g, q); }
         }
-        __syncthreads();
+        role_sync();
     }
 }
 
