@@ -241,8 +241,6 @@ __device__ __forceinline__ bool chol_inv32(double *As, double *Li, int lane) {
         __syncwarp();
         if (blockIdx.x == 0 && lane == 0) {
             const long long tp3 = clock64();
-            atomicAdd(&g_prof[13], (unsigned long long)(tp1 - tp0));
-            atomicAdd(&g_prof[14], (unsigned long long)(tp2 - tp1));
             atomicAdd(&g_prof[8], (unsigned long long)(tp3 - tp2));
         }
     }
@@ -304,24 +302,37 @@ __device__ __forceinline__ void s_update(double (&sacc)[2][4][2], const double *
 // (every warp arrives convergently; __syncthreads() in role-divergent code is flagged by compute-sanitizer synccheck).
 __device__ __forceinline__ void role_sync() { named_bar_sync(10, PD_THREADS); }
 
-// ---- one 8-row block of  X Linv^T  (Linv lower triangular: k blocks K <= j), in place in the shared tile X and
-//      to the HBM tile gx (pitch LTP).  Used for F_I = FW_I Linv_I^T. ----
-__device__ __forceinline__ void rowblock_times_linvT(double *X, const double *Li, double *__restrict__ gx, int rb, int g, int q) {
-    double a[8];
+// ---- X Linv^T for nrb row blocks starting at rb0 (Linv lower triangular: k blocks K <= j), in place in the shared tile X
+//      and to the HBM tile gx (pitch LTP).  Used for F_I = FW_I Linv_I^T.  The 20 B fragments of Linv are the same for
+//      every row block: loaded once. ----
+__device__ __forceinline__ void rows_times_linvT(double *X, const double *Li, double *__restrict__ gx, int rb0, int nrb, int g, int q) {
+    double b[4][8];
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) a[ks] = X[(8 * rb + g) * TP + 4 * ks + q];
-    __syncwarp();
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        double c2[2] = {0.0, 0.0};
+        for (int ks = 0; ks < 2 * (j + 1); ++ks) b[j][ks] = Li[(8 * j + g) * TP + 4 * ks + q];
+#pragma unroll 1
+    for (int rb = rb0; rb < rb0 + nrb; ++rb) {
+        double a[8];
 #pragma unroll
-        for (int K = 0; K <= j; ++K)
+        for (int ks = 0; ks < 8; ++ks) a[ks] = X[(8 * rb + g) * TP + 4 * ks + q];
+        __syncwarp();
+        double c2[4][2];
 #pragma unroll
-            for (int s = 0; s < 2; ++s) dmma(c2, a[2 * K + s], Li[(8 * j + g) * TP + 8 * K + 4 * s + q]);
-        const int r = 8 * rb + g, c = 8 * j + 2 * q;
-        *reinterpret_cast<double2 *>(&X[r * TP + c]) = make_double2(c2[0], c2[1]);
-        __stcs(&gx[r * LTP + c], c2[0]);
-        __stcs(&gx[r * LTP + c + 1], c2[1]);
+        for (int j = 0; j < 4; ++j) { c2[j][0] = 0.0; c2[j][1] = 0.0; }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (ks < 2 * (j + 1)) dmma(c2[j], a[ks], b[j][ks]);      // the four column blocks are independent chains
+        const int r = 8 * rb + g;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = 8 * j + 2 * q;
+            *reinterpret_cast<double2 *>(&X[r * TP + c]) = make_double2(c2[j][0], c2[j][1]);
+            __stcs(&gx[r * LTP + c], c2[j][0]);
+            __stcs(&gx[r * LTP + c + 1], c2[j][1]);
+        }
     }
 }
 
@@ -353,8 +364,7 @@ __device__ __noinline__ bool factor_chain(PdShared &sh, double *__restrict__ til
             if (I < nb) {
                 // ---- F_I = FW_I Linv_I^T, in place in the shared F tile and to HBM ----
                 double *gf = gt + LT_TILE;
-#pragma unroll 1
-                for (int rb = 0; rb < 4; ++rb) rowblock_times_linvT(sh.Fa, sh.Li, gf, rb, g, q);
+                rows_times_linvT(sh.Fa, sh.Li, gf, 0, 4, g, q);
             }
         }
         const long long tS2 = clock64();
@@ -507,9 +517,12 @@ __device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict_
         if (I + 1 < nb) {
             // ---- T_{I+1} = B_I Linv_I^T (band rows of block I, coupling part) ----
             double *gn = tiles + (size_t)(I + 1) * BLK_TILES;
+            const long long tw1 = clock64();
             if (warp == 1) coupling_rowblock<0>(sh, gn, base, NA, g, q);
             else { coupling_rowblock<1>(sh, gn, base, NA, g, q); coupling_rowblock<2>(sh, gn, base, NA, g, q); coupling_rowblock<3>(sh, gn, base, NA, g, q); }
             named_bar_sync(1, 64);       // T complete; nobody reads the band rows of block I any more
+            const long long tw2 = clock64();
+            if (blockIdx.x == 0 && threadIdx.x == 32) atomicAdd(&g_prof[13], (unsigned long long)(tw2 - tw1));
 #pragma unroll
             for (int t = 0; t < 17; ++t) sh.band[(warp - 1) * 544 + 32 * t + lane] = breg[t];
             __syncwarp();
@@ -525,6 +538,7 @@ __device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict_
             // ---- A'_{I+1} = A + D - T T^T ----
             if (warp == 1) { assemble_rowblock<0>(sh, base + 32, NA, true, g, q); assemble_rowblock<1>(sh, base + 32, NA, true, g, q); }
             else           { assemble_rowblock<2>(sh, base + 32, NA, true, g, q); assemble_rowblock<3>(sh, base + 32, NA, true, g, q); }
+            if (blockIdx.x == 0 && threadIdx.x == 32) atomicAdd(&g_prof[14], (unsigned long long)(clock64() - tw2));
         }
         role_sync();
     }
