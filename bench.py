@@ -113,12 +113,18 @@ def run_b200(args) -> dict:
     status_host = torch.empty((s1 - s0,), dtype=torch.int32).pin_memory()
 
     ws = B_._workspace("mincurv", lib.mc_mincurv_workspace_bytes(s1 - s0, n), dev)
-    ev = {"pdip": [], "setup": []}      # one CUDA-event pair per timed step, recorded on the launching stream
+    ev = {"pdip": [], "setup": [], "splines": [], "raceline": []}   # one CUDA-event pair per timed step, on the launching stream
     state = {}
 
     def step(rt_dev, timed_kernels: bool):
         """One pass of the hot path; returns dict of device results (all launches on the current stream)."""
+        if timed_kernels:
+            for k in ev:
+                ev[k].append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+            ev["splines"][-1][0].record()
         cx, cy, nv, h = B_.calc_splines_batch(rt_dev, want_coeffs=False)
+        if timed_kernels:
+            ev["splines"][-1][1].record()
         Bq = rt_dev.shape[0]
         alpha = torch.empty((Bq, n), dtype=torch.float64, device=dev)
         cerr = torch.empty((Bq,), dtype=torch.float64, device=dev)
@@ -128,8 +134,6 @@ def run_b200(args) -> dict:
         p = B_._ptr
         s = B_._stream()
         if timed_kernels:
-            for k in ev:
-                ev[k].append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
             ev["setup"][-1][0].record()
         _lib.check(lib.mc_mincurv_setup_batch(Bq, n, None, p(rt_dev), p(nv), p(h), W_VEH, None, p(st), p(ws), ws.numel(), s), "setup")
         if timed_kernels:
@@ -143,7 +147,11 @@ def run_b200(args) -> dict:
         # status words and returns) + re-evaluation -- together the five launches of mc_mincurv_solve_batch
         _lib.check(lib.mc_mincurv_kappa_batch(Bq, n, None, KAPPA_BOUND, p(alpha), p(st), p(iters), p(ws), ws.numel(), s), "kappa")
         _lib.check(lib.mc_mincurv_finalize_batch(Bq, n, None, p(alpha), KAPPA_BOUND, p(cerr), p(kmax), p(st), p(ws), ws.numel(), s), "finalize")
+        if timed_kernels:
+            ev["raceline"][-1][0].record()
         rl = B_.create_raceline_batch(rt_dev, nv, alpha, STEP_INTERP, n_out_max=n_out_max, with_head_curv=True)
+        if timed_kernels:
+            ev["raceline"][-1][1].record()
         return dict(alpha=alpha, status=st, iters=iters, kappa=rl["kappa"], raceline=rl["raceline_interp"], n_out=rl["n_out"])
 
     def sync_all():
@@ -173,6 +181,8 @@ def run_b200(args) -> dict:
     # average launch duration of the dominant kernels over the timed steps (CUDA events on the launching stream)
     pdip_last = float(np.mean([a.elapsed_time(b) for a, b in ev["pdip"]]))
     setup_last = float(np.mean([a.elapsed_time(b) for a, b in ev["setup"]]))
+    splines_last = float(np.mean([a.elapsed_time(b) for a, b in ev["splines"]]))
+    raceline_last = float(np.mean([a.elapsed_time(b) for a, b in ev["raceline"]]))
     tmax = torch.tensor([ms_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -219,6 +229,15 @@ def run_b200(args) -> dict:
         traffic = float(prof["dram_bytes_per_qp"]) * (s1 - s0)
     except Exception:
         pass
+    # per-kernel HBM roofline fractions (SURVEY 8d algorithmic bytes: K1 96 B/point; K2 = assembly + solve 40 B/point;
+    # K3 40 B/point in + 40 B per raceline station out), each over its own event-timed duration
+    n_stations = float(res["n_out"].double().mean().item())
+    def _k(name, bytes_per_qp, ms):
+        gbs = bytes_per_qp * (s1 - s0) / (ms * 1e-3) / 1e9
+        return {"kernel": name, "ms": ms, "algorithmic_bytes_per_qp": bytes_per_qp, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak}
+    per_kernel = [_k("calc_splines_kernel", 96.0 * n, splines_last),
+                  _k("mincurv_setup_kernel + mincurv_pdip_kernel", ALG_BYTES_PER_POINT_K2 * n, setup_last + pdip_last),
+                  _k("create_raceline_kernel (+ psi/kappa)", 40.0 * n + 40.0 * n_stations, raceline_last)]
     line = {
         "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -237,7 +256,7 @@ def run_b200(args) -> dict:
         "roofline": {"bound": "hbm", "kernel": "mincurv_pdip_kernel", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                     "kernel_ms": pdip_last, "setup_kernel_ms": setup_last,
+                     "kernel_ms": pdip_last, "setup_kernel_ms": setup_last, "per_kernel": per_kernel,
                      "algorithmic_bytes_per_launch": alg_bytes,
                      # implementation traffic (ncu dram bytes per QP x QPs of this launch) over the live kernel time
                      "traffic_gbs": (traffic / (pdip_last * 1e-3) / 1e9) if traffic else None,
