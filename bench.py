@@ -100,6 +100,9 @@ def run_b200(args) -> dict:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # rank 0 must print exactly one line: some images export NCCL_DEBUG=VERSION, which makes NCCL write its banner to stdout
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     n, bl = args.npoints, args.batch
