@@ -32,7 +32,6 @@ constexpr int LTP = 33;            // pitch of the packed (Linv | T) tile in HBM
 constexpr int LT_TILE = 32 * LTP;  // packed (Linv lower | T upper, shifted one column right)
 constexpr int F_TILE = 32 * LTP;   // F_I, row-major
 constexpr int BLK_TILES = LT_TILE + F_TILE;   // doubles per chain block in the slab (one contiguous bulk copy)
-constexpr unsigned BLK_BYTES = BLK_TILES * sizeof(double);
 constexpr unsigned LT_BYTES = LT_TILE * sizeof(double);
 constexpr int RING = 6;            // half-block slots (one packed LT tile or one F tile each) of the sweep ring.  Even, so that
                                    // LT tiles only ever use even slots and F tiles odd ones: every slot has ONE consumer warp,

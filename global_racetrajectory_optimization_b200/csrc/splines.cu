@@ -130,7 +130,6 @@ create_raceline_kernel(int n_max, const int32_t *__restrict__ n_pts, const doubl
     const int b = blockIdx.x;
     const int n = n_pts ? n_pts[b] : n_max;
     __shared__ double s_part[256];
-    __shared__ double s_tot;
     if (n < 3 || n > n_max) { if (threadIdx.x == 0) n_out[b] = 0; return; }
     const int np = spl_np(n_max);
     double *sv = ws + (size_t)b * S_NUM * np;
@@ -177,7 +176,6 @@ create_raceline_kernel(int n_max, const int32_t *__restrict__ n_pts, const doubl
     if (threadIdx.x == 0) {
         double run = 0.0;
         for (int t = 0; t < (int)blockDim.x; ++t) { const double v = s_part[t]; s_part[t] = run; run += v; }
-        s_tot = run;
     }
     __syncthreads();
     double run = s_part[threadIdx.x];
