@@ -335,40 +335,16 @@ __device__ __forceinline__ void rows_times_linvT(double *X, const double *Li, do
     }
 }
 
-// ---- 32x32 triangular mat-vec over a factorisation tile in shared memory (row-major, pitch TP) on the tensor cores:
-//      the matrix is the A operand (8x4 sub-tiles, conflict-free at pitch 36), the vector the B operand with all
-//      eight columns equal, so every lane of quad g ends with out[8 I + g] in acc[I].  Used to run the predictor's
-//      forward substitution inside the factorisation, where Linv_I and T_I are still in shared memory
-//      (vf[ks] = v[4 ks + q]).  LOWER: sub-tiles with k-block <= row block (Linv, explicit zeros above the diagonal);
-//      otherwise sub-tiles with k-block >= row block (T; the blocks left of the diagonal are never written). ----
-template <bool LOWER>
-__device__ __forceinline__ void tile_matvec(double (&acc)[4], const double *M, const double (&vf)[8], int g, int q) {
-    double c2[4][2];
-#pragma unroll
-    for (int I = 0; I < 4; ++I) { c2[I][0] = acc[I]; c2[I][1] = 0.0; }
-#pragma unroll
-    for (int ks = 0; ks < 8; ++ks)
-#pragma unroll
-        for (int I = 0; I < 4; ++I)
-            if (LOWER ? (ks <= 2 * I + 1) : (ks >= 2 * I)) dmma(c2[I], M[(8 * I + g) * TP + 4 * ks + q], vf[ks]);
-#pragma unroll
-    for (int I = 0; I < 4; ++I) acc[I] = c2[I][0];
-}
-
 // ---- warp 0: the chain.  Rounds I = 0..nb-1 are the chain blocks, round nb the separator block.
 //      Phase A: Cholesky + inverse of the block the fill warps assembled into As.
 //      Phase B: Linv_I and F_I = FW_I Linv_I^T to the HBM tiles (the fill warps build T_{I+1} and A'_{I+1}). ----
-__device__ __noinline__ bool factor_chain(PdShared &sh, double *__restrict__ tiles, const double *__restrict__ gfw,
-                                          double *__restrict__ ypad, int n, int nb) {
+__device__ __noinline__ bool factor_chain(PdShared &sh, double *__restrict__ tiles, int n, int nb) {
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
     bool ok = true;
     role_sync();                      // the fill warps have assembled A'_0 into As
-    const int NA = n - 32;
     for (int I = 0; I <= nb; ++I) {
         // =========================== phase A ===========================
-        double gI = 0.0;                                  // fused forward substitution: right-hand side of this block
-        if (gfw && I < nb) { const int nd = 32 * I + (threadIdx.x & 31); if (nd < NA) gI = gfw[nd]; }
         if (I == nb) named_bar_sync(3, PD_THREADS);      // the fill warps have put the separator Schur complement into As
         const long long tB = clock64();
         ok = chol_inv32(sh.As, sh.Li, lane) && ok;
@@ -388,22 +364,6 @@ __device__ __noinline__ bool factor_chain(PdShared &sh, double *__restrict__ til
                 // ---- F_I = FW_I Linv_I^T, in place in the shared F tile and to HBM ----
                 double *gf = gt + LT_TILE;
                 rows_times_linvT(sh.Fa, sh.Li, gf, 0, 4, g, q);
-                if (gfw) {
-                    // ---- fused forward substitution of the predictor: y_I = Linv_I (g_I - T_I y_{I-1}); warp 2 left
-                    //      u_I = T_I y_{I-1} in ubuf during phase A ----
-                    double *tb = sh.vbuf[1], *ybuf = sh.vbuf[5];
-                    const double *ubuf = sh.vbuf[6];
-                    tb[lane] = (I > 0) ? gI - ubuf[lane] : gI;
-                    __syncwarp();
-                    double vf[8], acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) vf[ks] = tb[4 * ks + q];
-                    tile_matvec<true>(acc, sh.Li, vf, g, q);
-                    if (q == 0) {
-#pragma unroll
-                        for (int J = 0; J < 4; ++J) { ybuf[8 * J + g] = acc[J]; ypad[32 * I + 8 * J + g] = acc[J]; }
-                    }
-                }
             }
         }
         const long long tS2 = clock64();
@@ -469,7 +429,7 @@ __device__ __forceinline__ void coupling_rowblock(PdShared &sh, double *__restri
 // ---- warps 1, 2: the two 16-row halves of the separator fill row (FW, S) in phase A; in phase B the coupling block
 //      T_{I+1}, the band rows of block I+1 and the next diagonal block A'_{I+1} (so warp 0 only ever factors) ----
 __device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict__ HB, const double *__restrict__ DD,
-                                        double *__restrict__ tiles, bool fwd, int n, int nb) {
+                                        double *__restrict__ tiles, int n, int nb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int NA = n - 32;
@@ -477,7 +437,6 @@ __device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict_
     double sacc[2][4][2];          // own 16 rows of the separator Schur complement (C fragments)
     double breg[17];               // half of the next block's band rows (1088 doubles = 2 x 32 x 17)
     double dreg = 0.0;             // ... and of its barrier diagonal D (lanes 0..15: one row each)
-    double gacc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};      // fused forward substitution: own 16 rows of sum_I F_I y_I
     double *Ft = sh.Fa;
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -503,14 +462,6 @@ __device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict_
         if (I == nb) {
             // last round: the pending S -= F_{nb-1} F_{nb-1}^T, then the separator is handed to warp 0 through As
             s_update(sacc, Ft, ib, g, q);
-            if (fwd) {
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    const double yk = sh.vbuf[5][4 * ks + q];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) dmma(gacc[i], Ft[(8 * (ib + i) + g) * TP + 4 * ks + q], yk);
-                }
-            }
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -530,25 +481,6 @@ __device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict_
                 for (int i = 0; i < 2; ++i)
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) a[i][ks] = Ft[(8 * (ib + i) + g) * TP + 4 * ks + q];
-                if (fwd) {
-                    // fused forward substitution: gS -= F_{I-1} y_{I-1} (own rows; the A fragments are the ones of FW) ...
-                    double vf[8];
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) vf[ks] = sh.vbuf[5][4 * ks + q];
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) dmma(gacc[i], a[i][ks], vf[ks]);
-                    if (warp == 2) {
-                        // ... and u_I = T_I y_{I-1} for warp 0's y_I = Linv_I (g_I - u_I) in phase B
-                        double u[4] = {0.0, 0.0, 0.0, 0.0};
-                        tile_matvec<false>(u, sh.Ts, vf, g, q);
-                        if (q == 0) {
-#pragma unroll
-                            for (int J = 0; J < 4; ++J) sh.vbuf[6][8 * J + g] = u[J];
-                        }
-                    }
-                }
             }
             named_bar_sync(1, 64);       // both fill warps are done reading F_{I-1}
             const bool hasY = (I == 0) || (base + 31 >= NA - 32);
@@ -609,17 +541,10 @@ __device__ __noinline__ void factor_fill(PdShared &sh, const double *__restrict_
         }
         role_sync();
     }
-    if (fwd && q == 0) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) sh.vbuf[4][8 * (ib + i) + g] = gacc[i][0];      // sum_I F_I y_I for the separator step of solve()
-    }
 }
 
-// gfw != nullptr: the forward substitution L y = gfw is run inside the factorisation (y to ypad, the separator sum to
-// vbuf[4]); the following solve() then starts at the separator (first = nb).
 __device__ __noinline__ bool factor(PdShared &sh, const double *__restrict__ HB, const double *__restrict__ DD,
-                                    double *__restrict__ tiles, const double *__restrict__ gfw, double *__restrict__ ypad,
-                                    int n, int nb) {
+                                    double *__restrict__ tiles, int n, int nb) {
     const int warp = threadIdx.x >> 5;
     const int NA = n - 32;
     // separator diagonal block C + D_S: gathered into As by all threads, then picked up as C fragments by the fill warps
@@ -639,9 +564,9 @@ __device__ __noinline__ bool factor(PdShared &sh, const double *__restrict__ HB,
     }
     __syncthreads();
     if (warp == 0) {
-        if (!factor_chain(sh, tiles, gfw, ypad, n, nb)) sh.flag = 1;
+        if (!factor_chain(sh, tiles, n, nb)) sh.flag = 1;
     } else {
-        factor_fill(sh, HB, DD, tiles, gfw != nullptr, n, nb);
+        factor_fill(sh, HB, DD, tiles, n, nb);
     }
     __syncthreads();
     return sh.flag == 0;
@@ -730,12 +655,10 @@ __device__ __forceinline__ double sm_f_mtv(const double *F, const double *v, int
 // numbers 2v (LT) and 2v+1 (F), slot = fill number % RING.  The new count is returned.
 // ------------------------------------------------------------------------------------------------
 __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ tiles, const double *__restrict__ g,
-                                       double *__restrict__ x, double *__restrict__ ypad, int n, int nb, unsigned fill, int first) {
+                                       double *__restrict__ x, double *__restrict__ ypad, int n, int nb, unsigned fill) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int NA = n - 32;
     double *ring = sh.band;
-    // first = 0: forward + separator + backward; first = nb: the forward substitution was run inside factor()
-    // (y in ypad, sum_I F_I y_I in gsum): start at the separator.  Visit i of the full sequence is ring visit fill + i - first.
     const unsigned nvis = 2u * nb + 1u;
     double *tb = sh.vbuf[1], *xb = sh.vbuf[0], *xs = sh.vbuf[3], *gsum = sh.vbuf[4];
     fence_proxy_async();        // the ring area was last written through the generic proxy (band rows, factor tiles)
@@ -744,10 +667,10 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
         // ---- producer: one elected thread issues the bulk copies ----
         if (lane == 0) {
             const uint64_t pol = l2_evict_first_policy();
-            for (unsigned i = first; i < nvis; ++i) {
+            for (unsigned i = 0; i < nvis; ++i) {
                 const unsigned blk = (i < (unsigned)nb) ? i : ((i == (unsigned)nb) ? (unsigned)nb : 2u * nb - i);
                 for (unsigned h = 0; h < 2; ++h) {      // (the separator has no F tile: its slot is copied but never read)
-                    const unsigned f = 2u * (fill + i - first) + h, sl = f % RING, k = f / RING;
+                    const unsigned f = 2u * (fill + i) + h, sl = f % RING, k = f / RING;
                     if (k > 0) mbar_wait_relaxed(&sh.empty_bar[sl], (k - 1) & 1u);
                     mbar_expect_tx(&sh.full_bar[sl], LT_BYTES);
                     tma_load_1d(ring + sl * LT_TILE, tiles + (size_t)blk * BLK_TILES + h * LT_TILE, LT_BYTES, &sh.full_bar[sl], pol);
@@ -758,8 +681,8 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
         // ---- separator-row mat-vecs, off the chain: forward gS -= F_I y_I (behind warp 0), backward c_I = F_I^T x_S
         //      (ahead of warp 0).  aux_bar[v & 3] / xch[v & 3] hand y_I / c_I over per visit v. ----
         double gacc = 0.0;
-        for (unsigned i = first; i < nvis; ++i) {
-            const unsigned v = fill + i - first, f = 2u * v + 1u, sl = f % RING, k = f / RING, a = v & 3u;
+        for (unsigned i = 0; i < nvis; ++i) {
+            const unsigned v = fill + i, f = 2u * v + 1u, sl = f % RING, k = f / RING, a = v & 3u;
             mbar_wait_relaxed(&sh.full_bar[sl], k & 1u);
             const double *Ft = ring + sl * LT_TILE;
             if (i < (unsigned)nb) {
@@ -784,8 +707,8 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
     } else {
         // ---- forward: y_I = Linv_I (g_I - T_I y_{I-1}) ----
         const long long tfw = clock64();
-        double gnext = (first == 0 && lane < NA) ? g[lane] : 0.0;
-        for (int I = first; I < nb; ++I) {
+        double gnext = (lane < NA) ? g[lane] : 0.0;
+        for (int I = 0; I < nb; ++I) {
             const unsigned v = fill + I, f = 2u * v, sl = f % RING, k = f / RING, a = v & 3u;
             const double gv = gnext;
             if (I + 1 < nb) { const int nd = 32 * (I + 1) + lane; gnext = (nd < NA) ? g[nd] : 0.0; }
@@ -807,10 +730,10 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
         const long long tsep = clock64();
         // ---- separator: x_S = LinvS^T LinvS (g_S - sum F_I y_I) ----
         {
-            const unsigned v = fill + nb - first, f = 2u * v, sl = f % RING, k = f / RING, a = v & 3u;
+            const unsigned v = fill + nb, f = 2u * v, sl = f % RING, k = f / RING, a = v & 3u;
             const double gs0 = g[NA + lane];
             mbar_wait(&sh.full_bar[sl], k & 1u);
-            if (first == 0) named_bar_sync(9, 64);      // warp 2 has published gsum (fused mode: factor() did, before its last barrier)
+            named_bar_sync(9, 64);
             const double *LS = ring + sl * LT_TILE;
             tb[lane] = gs0 - gsum[lane];
             __syncwarp();
@@ -830,7 +753,7 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
         double ynext = ypad[32 * (nb - 1) + lane];
         for (int i = 0; i < nb; ++i) {
             const int I = nb - 1 - i;
-            const unsigned v = fill + nb + 1 + i - first, f = 2u * v, sl = f % RING, k = f / RING, a = v & 3u;
+            const unsigned v = fill + nb + 1 + i, f = 2u * v, sl = f % RING, k = f / RING, a = v & 3u;
             const double yv = ynext;
             if (I > 0) ynext = ypad[32 * (I - 1) + lane];
             const long long tw = clock64();
@@ -853,7 +776,7 @@ __device__ __noinline__ unsigned solve(PdShared &sh, const double *__restrict__ 
     const long long tend = clock64();
     __syncthreads();
     PROF_ADD(23, tend);
-    return fill + nvis - first;
+    return fill + nvis;
 }
 
 // banded cyclic mat-vec out = H v (real-indexed)
@@ -980,10 +903,10 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             __syncthreads();
             PROF_ADD(16, tv1);
             const long long tf0 = clock64();
-            if (!factor(sh, HB, DD, tiles, RHS, YP, n, nb)) { result = 3; break; }     // + forward substitution of the predictor
+            if (!factor(sh, HB, DD, tiles, n, nb)) { result = 3; break; }
             PROF_ADD(10, tf0);
             const long long ts0 = clock64();
-            fill = solve(sh, tiles, RHS, DX, YP, n, nb, fill, nb);
+            fill = solve(sh, tiles, RHS, DX, YP, n, nb, fill);
             PROF_ADD(6, ts0);
             // ---- affine direction: step lengths 1 / max-ratio; mu_aff as a polynomial in (ap, ad) ----
             const long long tv2 = clock64();
@@ -1045,7 +968,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
             __syncthreads();
             PROF_ADD(18, tv3);
             const long long ts1 = clock64();
-            fill = solve(sh, tiles, RHS, DX, YP, n, nb, fill, 0);
+            fill = solve(sh, tiles, RHS, DX, YP, n, nb, fill);
             PROF_ADD(6, ts1);
             const long long tv4 = clock64();
             rp = 0.0; rdl = 0.0;
@@ -1242,12 +1165,12 @@ mincurv_pdip_kappa_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, d
             apply_Et(slab, L, n, VV, ETV, t0, t1, t2, t3, t4, t5);
             for (int i = threadIdx.x; i < n; i += PD_THREADS) RHS[i] = -F[i] - ETV[i];
             __syncthreads();
-            if (!factor(sh, HB, DD, tiles, nullptr, nullptr, n, nb)) {
+            if (!factor(sh, HB, DD, tiles, n, nb)) {
                 // E^T W E with W = l/s -> 1e12 and beyond is no longer numerically SPD: accept a late iterate, else give up
                 result = (mu <= 1e-7 * mu0 && rdmax <= 1e3 * rd_tol && rpmax <= 1e-6 * kb) ? 0 : 3;
                 break;
             }
-            fill = solve(sh, tiles, RHS, DX, YP, n, nb, fill, 0);
+            fill = solve(sh, tiles, RHS, DX, YP, n, nb, fill);
             apply_E(slab, L, n, DX, EDX, t0, t1, t2, t3, t4, t5);
             // ---- affine step lengths and centring ----
             double rp = 0.0, rdl = 0.0, c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
@@ -1292,7 +1215,7 @@ mincurv_pdip_kappa_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, d
             apply_Et(slab, L, n, VV, ETV, t0, t1, t2, t3, t4, t5);
             for (int i = threadIdx.x; i < n; i += PD_THREADS) RHS[i] -= ETV[i];
             __syncthreads();
-            fill = solve(sh, tiles, RHS, DX, YP, n, nb, fill, 0);
+            fill = solve(sh, tiles, RHS, DX, YP, n, nb, fill);
             apply_E(slab, L, n, DX, EDX, t0, t1, t2, t3, t4, t5);
             rp = 0.0; rdl = 0.0;
             for (int i = threadIdx.x; i < n; i += PD_THREADS) {
