@@ -279,7 +279,9 @@ __device__ __forceinline__ bool chol_inv32(double *As, double *Li, int lane) {
     return ok;
 }
 
-// S[own 16 rows][:] -= F[own rows][:] F^T  (rolled over the four 8-wide k blocks to keep the code small)
+// S[own 16 rows][:] -= F[own rows][:] F^T  (rolled over the four 8-wide k blocks to keep the code small).  S is
+// symmetric and chol_inv32 reads its lower triangle only: the blocks right of the diagonal are skipped (10 of the
+// 16 block products; their accumulators keep stale values that nobody reads).
 __device__ __forceinline__ void s_update(double (&sacc)[2][4][2], const double *Ft, int ib, int g, int q) {
 #pragma unroll 1
     for (int ks = 0; ks < 8; ++ks) {
@@ -291,7 +293,8 @@ __device__ __forceinline__ void s_update(double (&sacc)[2][4][2], const double *
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dmma(sacc[i][j], a[i], b[j]);
+            for (int j = 0; j < 4; ++j)
+                if (j <= ib + i) dmma(sacc[i][j], a[i], b[j]);
     }
 }
 
