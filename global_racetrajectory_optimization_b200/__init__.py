@@ -4,8 +4,9 @@
 /root/reference/main_globaltraj.py uses on its mincurv / mincurv_iqp / shortest_path branches
 (``tph.opt_min_curv.opt_min_curv(...)`` etc.); ``batch`` holds the batched device API.
 """
-from . import (batch, calc_head_curv_an, calc_splines, create_raceline, iqp_handler,  # noqa: F401
-               opt_min_curv, opt_shortest_path, synth)
+from . import (batch, calc_ax_profile, calc_head_curv_an, calc_splines, calc_t_profile,  # noqa: F401
+               calc_vel_profile, create_raceline, import_veh_dyn_info, iqp_handler, opt_min_curv,
+               opt_shortest_path, synth)
 from .spline_system import SplineSystem  # noqa: F401
 
 __version__ = "0.1.0"

@@ -36,6 +36,10 @@ _SIGS = {
     "mc_iqp_relinearise_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_dbl, _c_int, _vp, _vp, _vp, _vp,
                                           _sz, _vp]),
     "mc_scale_alpha_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _c_dbl, _vp]),
+    "mc_vel_profile_workspace_bytes": (_sz, [_c_int, _c_int, _c_int]),
+    "mc_vel_profile_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _c_dbl, _c_int, _vp, _c_int, _vp,
+                                      _c_dbl, _c_dbl, _c_dbl, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mc_calc_ax_t_profile_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _c_int, _vp, _vp, _c_dbl, _vp, _vp, _vp]),
     "mc_debug_read_profile": (_c_int, [_vp, _c_int]),
 }
 

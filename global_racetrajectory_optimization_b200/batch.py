@@ -368,3 +368,128 @@ def iqp_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, ka
         h = torch.ones((B, n_cap), dtype=torch.float64, device=dev)   # use_dist_scaling=False from iteration 2 on
     fin["qp_solves"] = qp_solves
     return fin
+
+
+# ------------------------------------------------------------------------------------------------
+# velocity-profile stage: tph.calc_vel_profile + calc_ax_profile + calc_t_profile
+# ------------------------------------------------------------------------------------------------
+def _table(t, cols: int, name: str, dev) -> torch.Tensor:
+    t = torch.as_tensor(t, dtype=torch.float64).to(dev).contiguous()
+    if t.ndim != 2 or t.shape[1] != cols:
+        raise RuntimeError({3: "ggv diagram must consist of the three columns [vx, ax_max, ay_max]!",
+                            2: "ax_max_machines must consist of the two columns [vx, ax_max_machines]!"}[cols])
+    if t.shape[0] > 256:
+        raise ValueError(f"{name}: at most 256 rows are supported")
+    return t
+
+
+def vel_profile_batch(kappa: torch.Tensor, el_lengths: torch.Tensor, ggv, ax_max_machines, v_max,
+                      drag_coeff: float, m_veh: float, dyn_model_exp: float = 1.0, filt_window: Optional[int] = None,
+                      mu: Optional[torch.Tensor] = None, n_pts: Optional[torch.Tensor] = None,
+                      ggv_scales=None, want_profiles: bool = True, max_chunk: Optional[int] = None) -> dict:
+    """Batched tph.calc_vel_profile (closed, ggv branch) + calc_ax_profile + calc_t_profile.
+
+    kappa, el_lengths: [B, n_max] device tensors (n_pts[b] valid entries), e.g. the ``kappa`` /
+    ``el_lengths_interp`` / ``n_out`` results of create_raceline_batch.  ``v_max`` is a float, or -- together with
+    ``ggv_scales`` -- a sequence of V per-variant values: variant v of every track runs with
+    ggv[:, 1:] * ggv_scales[v] and top speed v_max[v] (one cell of the reference's lap-time matrix,
+    /root/reference/main_globaltraj.py:442-496).  Returns dict(laptime [B, V], status [B, V] and, if want_profiles,
+    vx [B, V, n_max], ax [B, V, n_max], t [B, V, n_max + 1])."""
+    _require_cuda()
+    lib = _lib.load()
+    kappa = _f64(kappa, "kappa")
+    el_lengths = _f64(el_lengths, "el_lengths")
+    B, n_max = kappa.shape
+    if el_lengths.shape != (B, n_max):
+        raise RuntimeError("kappa and el_lengths must have the same length if closed!")
+    dev = kappa.device
+    if mu is not None:
+        mu = _f64(mu, "mu")
+        if mu.shape != (B, n_max):
+            raise RuntimeError("kappa and mu must have the same length!")
+    n_pts = _npts(n_pts, B, dev)
+    ggv_t = _table(ggv, 3, "ggv", dev)
+    mach_t = _table(ax_max_machines, 2, "ax_max_machines", dev)
+    if filt_window is not None and int(filt_window) % 2 != 1:
+        raise RuntimeError("Window width of moving average filter must be odd!")
+    fw = 0 if filt_window is None else int(filt_window)
+    vmax_t = scale_t = None
+    per_variant = ggv_scales is not None or isinstance(v_max, torch.Tensor) or hasattr(v_max, "__len__")
+    if per_variant:
+        vm = torch.as_tensor(v_max, dtype=torch.float64).reshape(-1)
+        sc = torch.ones_like(vm) if ggv_scales is None else torch.as_tensor(ggv_scales, dtype=torch.float64).reshape(-1)
+        if vm.numel() == 1 and sc.numel() > 1:
+            vm = vm.expand(sc.numel()).clone()
+        if sc.numel() != vm.numel():
+            raise ValueError("v_max and ggv_scales must have one entry per variant")
+        V = int(vm.numel())
+        vmax_t, scale_t = vm.to(dev).contiguous(), sc.to(dev).contiguous()
+        v_hi, v_scalar = float(vm.max().item()), 0.0
+    else:
+        V, v_hi, v_scalar = 1, float(v_max), float(v_max)
+    # tph's range checks (the tables must cover the whole velocity range of the car)
+    if float(mach_t[-1, 0].item()) < v_hi:
+        raise RuntimeError("ax_max_machines has to cover the entire velocity range of the car (i.e. >= v_max)!")
+    if float(ggv_t[-1, 0].item()) < v_hi:
+        raise RuntimeError("ggv has to cover the entire velocity range of the car (i.e. >= v_max)!")
+    f64 = dict(dtype=torch.float64, device=dev)
+    laptime = torch.zeros((B, V), **f64)
+    status = torch.zeros((B, V), dtype=torch.int32, device=dev)
+    vx = torch.zeros((B, V, n_max), **f64) if want_profiles else None
+    ax = torch.zeros((B, V, n_max), **f64) if want_profiles else None
+    t = torch.zeros((B, V, n_max + 1), **f64) if want_profiles else None
+    per_track = lib.mc_vel_profile_workspace_bytes(1, V, n_max)
+    chunk = _chunk(B, per_track, dev) if max_chunk is None else min(B, int(max_chunk))
+    chunk = max(1, min(chunk, (2 ** 31 - 1024) // V))
+    ws = _workspace("velprofile", lib.mc_vel_profile_workspace_bytes(chunk, V, n_max), dev)
+    for s in range(0, B, chunk):
+        e = min(B, s + chunk)
+        rc = lib.mc_vel_profile_batch(e - s, n_max, _ptr(n_pts[s:e]) if n_pts is not None else None, _ptr(kappa[s:e]),
+                                      _ptr(el_lengths[s:e]), _ptr(mu[s:e]) if mu is not None else None, V, _ptr(scale_t),
+                                      _ptr(vmax_t), v_scalar, int(ggv_t.shape[0]), _ptr(ggv_t), int(mach_t.shape[0]),
+                                      _ptr(mach_t), float(dyn_model_exp), float(drag_coeff), float(m_veh), fw,
+                                      _ptr(vx[s:e]) if vx is not None else None, _ptr(ax[s:e]) if ax is not None else None,
+                                      _ptr(t[s:e]) if t is not None else None, _ptr(laptime[s:e]), _ptr(status[s:e]),
+                                      _ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, "mc_vel_profile_batch")
+    out = dict(laptime=laptime, status=status)
+    if want_profiles:
+        out.update(vx=vx, ax=ax, t=t)
+    return out
+
+
+def lap_time_matrix_batch(kappa: torch.Tensor, el_lengths: torch.Tensor, ggv, ax_max_machines, ggv_scales, top_speeds,
+                          drag_coeff: float, m_veh: float, dyn_model_exp: float = 1.0,
+                          filt_window: Optional[int] = None, n_pts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The lap-time matrix of /root/reference/main_globaltraj.py:442-496 for every track of the batch in one launch:
+    returns [B, len(top_speeds), len(ggv_scales)] lap times (top speeds in m/s)."""
+    ts = torch.as_tensor(top_speeds, dtype=torch.float64).reshape(-1)
+    gs = torch.as_tensor(ggv_scales, dtype=torch.float64).reshape(-1)
+    vm = ts.repeat_interleave(gs.numel())
+    sc = gs.repeat(ts.numel())
+    res = vel_profile_batch(kappa, el_lengths, ggv, ax_max_machines, vm, drag_coeff, m_veh, dyn_model_exp, filt_window,
+                            n_pts=n_pts, ggv_scales=sc, want_profiles=False)
+    bad_ = res["status"] != 0
+    if bool(bad_.any().item()):
+        raise RuntimeError("lap_time_matrix_batch: non-finite lap time for %i profile(s)" % int(bad_.sum().item()))
+    return res["laptime"].reshape(kappa.shape[0], ts.numel(), gs.numel())
+
+
+def calc_ax_t_profile_batch(vx: torch.Tensor, el_lengths: torch.Tensor, ax_in: Optional[torch.Tensor] = None,
+                            t_start: float = 0.0, n_pts: Optional[torch.Tensor] = None, want_t: bool = True):
+    """Stand-alone tph.calc_ax_profile (ax_in None: vx holds n + 1 values per row) / tph.calc_t_profile.
+    Returns (ax [P, n_max], t [P, n_max + 1] or None)."""
+    _require_cuda()
+    lib = _lib.load()
+    vx = _f64(vx, "vx")
+    el_lengths = _f64(el_lengths, "el_lengths")
+    P, n_max = el_lengths.shape
+    dev = vx.device
+    if ax_in is not None:
+        ax_in = _f64(ax_in, "ax_in")
+    ax_out = torch.zeros((P, n_max), dtype=torch.float64, device=dev)
+    t_out = torch.zeros((P, n_max + 1), dtype=torch.float64, device=dev) if want_t else None
+    rc = lib.mc_calc_ax_t_profile_batch(P, n_max, _ptr(_npts(n_pts, P, dev)), _ptr(vx), int(vx.shape[1]), _ptr(el_lengths),
+                                        _ptr(ax_in), float(t_start), _ptr(ax_out), _ptr(t_out), _stream())
+    _lib.check(rc, "mc_calc_ax_t_profile_batch")
+    return ax_out, t_out

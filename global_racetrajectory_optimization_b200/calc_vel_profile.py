@@ -1,0 +1,2 @@
+"""Drop-in module for ``trajectory_planning_helpers.calc_vel_profile`` (see tph_api.py for the reference call sites)."""
+from .tph_api import calc_vel_profile  # noqa: F401

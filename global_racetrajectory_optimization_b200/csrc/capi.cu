@@ -33,6 +33,12 @@ void launch_scale_alpha(int, int, double *, const double *, double, cudaStream_t
 size_t shortest_path_ws_doubles(int n_max);
 int launch_shortest_path(int, int, const int32_t *, const double *, const double *, double, const double *, double *,
                          int32_t *, int32_t *, double *, cudaStream_t);
+size_t vel_profile_ws_doubles(int n_max);
+int launch_vel_profile(int, int, int, const int32_t *, const double *, const double *, const double *, const double *,
+                       const double *, double, int, const double *, int, const double *, double, double, double, int,
+                       double *, double *, double *, double *, int32_t *, double *, cudaStream_t);
+void launch_ax_t_profile(int, int, const int32_t *, const double *, int, const double *, const double *, double, double *,
+                         double *, cudaStream_t);
 }  // namespace mc
 
 static thread_local char g_err[256] = "";
@@ -314,6 +320,43 @@ int mc_iqp_relinearise_batch(int B, int n_max, const int32_t *n_pts, const int32
 
 /* debug aid: cycle counters of CTA 0 of mincurv_pdip_kernel (16 x uint64): 0 A' assembly, 1 chol, 2 inverse,
  * 3 barrier A, 4 phase B, 5 barrier B, 6 solves, 7 TMA waits (forward), 9 total, 10 factor, 11 QPs, 12 IPM iterations */
+// ------------------------------------------------------------------------------------------------
+size_t mc_vel_profile_workspace_bytes(int B, int V, int n_max) {
+    if (B <= 0 || V <= 0 || n_max < 2) return 0;
+    return align256((size_t)B * V * mc::vel_profile_ws_doubles(n_max) * sizeof(double));
+}
+
+int mc_vel_profile_batch(int B, int n_max, const int32_t *n_pts, const double *kappa, const double *el_lengths,
+                         const double *mu, int V, const double *ggv_scale, const double *v_max_batch, double v_max,
+                         int n_ggv, const double *ggv, int n_mach, const double *ax_max_machines, double dyn_model_exp,
+                         double drag_coeff, double m_veh, int filt_window, double *vx, double *ax, double *t,
+                         double *laptime, int32_t *status, void *workspace, size_t workspace_bytes, void *stream) {
+    if (B <= 0 || V <= 0 || n_max < 2 || !kappa || !el_lengths || !ggv || !ax_max_machines || !laptime || n_ggv < 1 ||
+        n_mach < 1 || !(m_veh > 0.0) || !(dyn_model_exp > 0.0) || (!v_max_batch && !(v_max > 0.0)))
+        return bad("mc_vel_profile_batch: bad argument");
+    if (filt_window > 1 && (filt_window % 2 == 0 || filt_window >= n_max))
+        return bad("mc_vel_profile_batch: filt_window must be odd (tph: 'Window width of moving average filter must be odd!')");
+    if ((size_t)B * V > (size_t)0x7fffffff - 256) return bad("mc_vel_profile_batch: too many profiles in one call");
+    if (!workspace || workspace_bytes < mc_vel_profile_workspace_bytes(B, V, n_max)) {
+        snprintf(g_err, sizeof(g_err), "mc_vel_profile_batch: workspace too small");
+        return MC_EWORKSPACE;
+    }
+    if (mc::launch_vel_profile(B, V, n_max, n_pts, kappa, el_lengths, mu, ggv_scale, v_max_batch, v_max, n_ggv, ggv, n_mach,
+                               ax_max_machines, dyn_model_exp, drag_coeff, m_veh, filt_window, vx, ax, t, laptime, status,
+                               (double *)workspace, (cudaStream_t)stream) != 0)
+        return bad("mc_vel_profile_batch: ggv / ax_max_machines tables are limited to 256 rows");
+    return check_cuda("vel_profile_kernel");
+}
+
+int mc_calc_ax_t_profile_batch(int P, int n_max, const int32_t *n_pts, const double *vx, int vx_pitch,
+                               const double *el_lengths, const double *ax_in, double t_start, double *ax_out,
+                               double *t_out, void *stream) {
+    if (P <= 0 || n_max < 1 || !vx || !el_lengths || (!ax_out && !t_out) || vx_pitch < n_max + (ax_in ? 0 : 1))
+        return bad("mc_calc_ax_t_profile_batch: bad argument");
+    mc::launch_ax_t_profile(P, n_max, n_pts, vx, vx_pitch, el_lengths, ax_in, t_start, ax_out, t_out, (cudaStream_t)stream);
+    return check_cuda("ax_t_profile_kernel");
+}
+
 int mc_debug_read_profile(unsigned long long *host_out16, int reset) {
     return mc::debug_read_profile(host_out16, reset) == 0 ? MC_OK : MC_ECUDA;
 }

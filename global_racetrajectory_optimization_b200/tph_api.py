@@ -7,6 +7,10 @@
     opt_shortest_path  main_globaltraj.py:286-290
     create_raceline    main_globaltraj.py:371-376
     calc_head_curv_an  main_globaltraj.py:383-387
+    calc_vel_profile   main_globaltraj.py:400-410, :469-479   (the stage after the path)
+    calc_ax_profile    main_globaltraj.py:413-416, :482-485
+    calc_t_profile     main_globaltraj.py:419-421, :488-490
+    import_veh_dyn_info main_globaltraj.py:211-213           (host-side CSV reader, no compute)
 
 numpy in / numpy out; every call runs the CUDA kernels through the C-ABI with a batch of one
 (no CPU fallback: without the extension or a GPU these functions raise)."""
@@ -148,3 +152,104 @@ def iqp_handler(reftrack: np.ndarray, normvectors: np.ndarray, A, kappa_bound: f
         print("Minimum curvature IQP: %i iterations, curv_error_max: %.4frad/m"
               % (int(res["outer_iters"][0].item()), float(res["curv_error_max"][0].item())))
     return (res["alpha"][0, :n].cpu().numpy(), res["reftrack"][0, :n].cpu().numpy(), res["normvec"][0, :n].cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------
+# velocity-profile stage
+# ------------------------------------------------------------------------------------------------
+def import_veh_dyn_info(ggv_import_path: str = None, ax_max_machines_import_path: str = None) -> tuple:
+    """tph.import_veh_dyn_info.import_veh_dyn_info -> (ggv [k, 3], ax_max_machines [m, 2]); host-side file reader
+    with tph's plausibility checks."""
+    ggv = None
+    if ggv_import_path is not None:
+        with open(ggv_import_path, "rb") as fh:
+            ggv = np.loadtxt(fh, comments="#", delimiter=",")
+        if ggv.ndim == 1:
+            ggv = np.expand_dims(ggv, 0)
+        if ggv.shape[1] != 3:
+            raise RuntimeError("ggv diagram must consist of the three columns [vx, ax_max, ay_max]!")
+        if np.any(ggv[:, 0] < 0.0) or np.any(ggv[:, 1:] > 50.0) or np.any(ggv[:, 1] < 0.0) or np.any(ggv[:, 2] < 0.0):
+            raise RuntimeError("ggv seems unreasonable!")
+    ax_max_machines = None
+    if ax_max_machines_import_path is not None:
+        with open(ax_max_machines_import_path, "rb") as fh:
+            ax_max_machines = np.loadtxt(fh, comments="#", delimiter=",")
+        if ax_max_machines.ndim == 1:
+            ax_max_machines = np.expand_dims(ax_max_machines, 0)
+        if ax_max_machines.shape[1] != 2:
+            raise RuntimeError("ax_max_machines must consist of the two columns [vx, ax_max_machines]!")
+        if np.any(ax_max_machines[:, 0] < 0.0) or np.any(ax_max_machines[:, 1] > 20.0) or np.any(ax_max_machines[:, 1] < 0.0):
+            raise RuntimeError("ax_max_machines seems unreasonable!")
+    return ggv, ax_max_machines
+
+
+def calc_vel_profile(ax_max_machines: np.ndarray, kappa: np.ndarray, el_lengths: np.ndarray, closed: bool,
+                     drag_coeff: float, m_veh: float, ggv: np.ndarray = None, loc_gg: np.ndarray = None,
+                     v_max: float = None, dyn_model_exp: float = 1.0, mu: np.ndarray = None, v_start: float = None,
+                     v_end: float = None, filt_window: int = None) -> np.ndarray:
+    """tph.calc_vel_profile.calc_vel_profile -> vx_profile (closed tracks, ggv branch)."""
+    if (ggv is not None or mu is not None) and loc_gg is not None:
+        raise RuntimeError("Either ggv and optionally mu OR loc_gg must be supplied, not both (or all) of them!")
+    if ggv is None and loc_gg is None:
+        raise RuntimeError("Either ggv or loc_gg must be supplied!")
+    if loc_gg is not None:
+        raise NotImplementedError("loc_gg is outside the B200 path; main_globaltraj.py passes a ggv diagram")
+    kappa = np.asarray(kappa, dtype=np.float64)
+    el_lengths = np.asarray(el_lengths, dtype=np.float64)
+    if mu is not None and kappa.size != np.asarray(mu).size:
+        raise RuntimeError("kappa and mu must have the same length!")
+    if closed and kappa.size != el_lengths.size:
+        raise RuntimeError("kappa and el_lengths must have the same length if closed!")
+    if not closed and kappa.size != el_lengths.size + 1:
+        raise RuntimeError("kappa must have the length of el_lengths + 1 if unclosed!")
+    if not closed and v_start is None:
+        raise RuntimeError("v_start must be provided for the unclosed case!")
+    if not closed:
+        raise NotImplementedError("open tracks (closed=False) are outside the B200 path; main_globaltraj.py passes closed=True")
+    ggv = np.asarray(ggv, dtype=np.float64)
+    ax_max_machines = np.asarray(ax_max_machines, dtype=np.float64)
+    if ax_max_machines.ndim != 2 or ax_max_machines.shape[1] != 2:
+        raise RuntimeError("ax_max_machines must consist of the two columns [vx, ax_max_machines]!")
+    if ggv.ndim != 2 or ggv.shape[1] != 3:
+        raise RuntimeError("ggv diagram must consist of the three columns [vx, ax_max, ay_max]!")
+    if v_max is None:
+        v_max = min(ggv[-1, 0], ax_max_machines[-1, 0])
+    if not 1.0 <= dyn_model_exp <= 2.0:
+        print("WARNING: Exponent for the vehicle dynamics model should be in the range [1.0, 2.0]!")
+    res = _b.vel_profile_batch(_up(kappa), _up(el_lengths), ggv, ax_max_machines, float(v_max), float(drag_coeff),
+                               float(m_veh), dyn_model_exp=float(dyn_model_exp), filt_window=filt_window,
+                               mu=_up(mu) if mu is not None else None)
+    return res["vx"][0, 0].cpu().numpy()
+
+
+def calc_ax_profile(vx_profile: np.ndarray, el_lengths: np.ndarray, eq_length_output: bool = False) -> np.ndarray:
+    """tph.calc_ax_profile.calc_ax_profile -> ax_profile."""
+    vx_profile = np.asarray(vx_profile, dtype=np.float64)
+    el_lengths = np.asarray(el_lengths, dtype=np.float64)
+    if vx_profile.size != el_lengths.size + 1:
+        raise RuntimeError("Array size of vx_profile should be 1 element bigger than el_lengths!")
+    ax, _ = _b.calc_ax_t_profile_batch(_up(vx_profile), _up(el_lengths), want_t=False)
+    ax = ax[0].cpu().numpy()
+    if eq_length_output:
+        return np.append(ax, 0.0)
+    return ax
+
+
+def calc_t_profile(vx_profile: np.ndarray, el_lengths: np.ndarray, t_start: float = 0.0,
+                   ax_profile: np.ndarray = None) -> np.ndarray:
+    """tph.calc_t_profile.calc_t_profile -> t_profile (el_lengths.size + 1 entries)."""
+    vx_profile = np.asarray(vx_profile, dtype=np.float64)
+    el_lengths = np.asarray(el_lengths, dtype=np.float64)
+    if vx_profile.size < el_lengths.size:
+        raise RuntimeError("vx_profile and el_lenghts must have at least the same length!")
+    if ax_profile is not None and np.asarray(ax_profile).size < el_lengths.size:
+        raise RuntimeError("ax_profile and el_lenghts must have at least the same length!")
+    n = el_lengths.size
+    if ax_profile is None:
+        if vx_profile.size < n + 1:       # tph's calc_ax_profile call raises in this case
+            raise RuntimeError("Array size of vx_profile should be 1 element bigger than el_lengths!")
+        _, t = _b.calc_ax_t_profile_batch(_up(vx_profile[:n + 1]), _up(el_lengths), t_start=float(t_start))
+    else:
+        ax_in = np.asarray(ax_profile, dtype=np.float64)[:n]
+        _, t = _b.calc_ax_t_profile_batch(_up(vx_profile[:n]), _up(el_lengths), ax_in=_up(ax_in), t_start=float(t_start))
+    return t[0].cpu().numpy()

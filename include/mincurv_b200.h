@@ -164,6 +164,40 @@ int mc_iqp_relinearise_batch(int B, int n_max, const int32_t *n_pts, const int32
  * `alpha *= iter / iters_min` of tph.iqp_handler. */
 int mc_scale_alpha_batch(int B, int n_max, double *alpha, const double *scale_batch, double scale, void *stream);
 
+/* -------------------------------------------------------------------------------------------------
+ * tph.calc_vel_profile.calc_vel_profile(ggv, ax_max_machines, v_max, kappa, el_lengths, closed=True, filt_window,
+ * dyn_model_exp, drag_coeff, m_veh[, mu]) followed by tph.calc_ax_profile.calc_ax_profile(vx_cl, el_lengths) and
+ * tph.calc_t_profile.calc_t_profile(vx, ax, el_lengths) -- call sites /root/reference/main_globaltraj.py:400-421
+ * -- for B closed racelines x V variants per raceline.  A variant is one cell of the reference's lap-time
+ * matrix (/root/reference/main_globaltraj.py:442-496): ggv_mod[:, 1:] = ggv[:, 1:] * ggv_scale[v], v_max = v_max_batch[v].
+ *   kappa, el_lengths [B][n_max] : curvature and element lengths of the (re-sampled) raceline, n_pts[b] valid entries
+ *                                  (the kappa / el_lengths_interp outputs of mc_create_raceline_batch, n_pts = n_out)
+ *   mu [B][n_max] or NULL        : friction scaling per point (NULL => ones)
+ *   ggv_scale [V] or NULL (=> 1), v_max_batch [V] or NULL (=> the scalar v_max)
+ *   ggv [n_ggv][3] (v, ax_max, ay_max), ax_max_machines [n_mach][2] (v, ax): device arrays, <= 256 rows each
+ *   filt_window                  : odd width of tph's moving-average filter, <= 1 => none (filt_window=None)
+ *   outputs (profile p = b * V + v): vx [B*V][n_max], ax [B*V][n_max], t [B*V][n_max + 1] (each may be NULL),
+ *   laptime [B*V] (= t[n_pts]), status [B*V] (0 ok, 3 non-finite result) or NULL
+ * workspace: mc_vel_profile_workspace_bytes(B, V, n_max)
+ */
+size_t mc_vel_profile_workspace_bytes(int B, int V, int n_max);
+int mc_vel_profile_batch(int B, int n_max, const int32_t *n_pts, const double *kappa, const double *el_lengths,
+                         const double *mu, int V, const double *ggv_scale, const double *v_max_batch, double v_max,
+                         int n_ggv, const double *ggv, int n_mach, const double *ax_max_machines,
+                         double dyn_model_exp, double drag_coeff, double m_veh, int filt_window,
+                         double *vx, double *ax, double *t, double *laptime, int32_t *status,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* tph.calc_ax_profile.calc_ax_profile(vx_profile, el_lengths, eq_length_output=False) and
+ * tph.calc_t_profile.calc_t_profile(vx_profile, el_lengths, t_start, ax_profile) stand-alone
+ * (call sites /root/reference/main_globaltraj.py:413-421) for P profiles.
+ *   vx [P][vx_pitch] (vx_pitch >= n_max + 1 when ax_in is NULL: ax is derived from vx[0..n]), el_lengths [P][n_max],
+ *   ax_in [P][n_max] or NULL, ax_out [P][n_max] or NULL, t_out [P][n_max + 1] or NULL (t_out[0] = t_start).
+ */
+int mc_calc_ax_t_profile_batch(int P, int n_max, const int32_t *n_pts, const double *vx, int vx_pitch,
+                               const double *el_lengths, const double *ax_in, double t_start,
+                               double *ax_out, double *t_out, void *stream);
+
 /* Debug aid (synchronous): reads (and optionally clears) 24 cycle counters that CTA 0 of mincurv_pdip_kernel
  * accumulates per phase -- used by tools/prof_run.py to attribute time inside the kernel. Host pointer. */
 int mc_debug_read_profile(unsigned long long *host_out24, int reset);

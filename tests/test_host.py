@@ -54,6 +54,18 @@ def test_workspace_queries_and_argument_validation_without_gpu():
                                       None, 0, None) == -3        # workspace too small
     assert lib.mc_create_raceline_batch(1, 100, None, dummy, 3, dummy, dummy, 2.0, 10, dummy, dummy, dummy, dummy, dummy,
                                         dummy, dummy, dummy, dummy, None, None, dummy, 1 << 30, None) == -1   # stride 3
+    # velocity-profile stage: workspace = 5 interleaved vectors per profile; validation before any CUDA call
+    assert lib.mc_vel_profile_workspace_bytes(3, 7, 1200) >= 3 * 7 * 5 * 1200 * 8
+    assert lib.mc_vel_profile_workspace_bytes(3, 7, 1200) % 256 == 0 and lib.mc_vel_profile_workspace_bytes(0, 7, 1200) == 0
+    vp = lambda **kw: lib.mc_vel_profile_batch(*[kw.get(k, d) for k, d in (
+        ("B", 1), ("n_max", 100), ("n_pts", None), ("kappa", dummy), ("el", dummy), ("mu", None), ("V", 1), ("scale", None),
+        ("vmb", None), ("v_max", 70.0), ("n_ggv", 4), ("ggv", dummy), ("n_mach", 4), ("mach", dummy), ("exp", 1.0),
+        ("drag", 0.75), ("m", 1200.0), ("filt", 0), ("vx", None), ("ax", None), ("t", None), ("lap", dummy), ("st", None),
+        ("ws", None), ("wsb", 0), ("stream", None))])
+    assert vp() == -3                                              # workspace too small
+    assert vp(kappa=None) == -1 and vp(lap=None) == -1 and vp(V=0) == -1 and vp(m=0.0) == -1 and vp(v_max=0.0) == -1
+    assert vp(filt=4) == -1 and b"must be odd" in lib.mc_last_error()
+    assert lib.mc_calc_ax_t_profile_batch(1, 100, None, dummy, 100, dummy, None, 0.0, dummy, None, None) == -1   # vx needs n + 1
 
 
 def test_spline_system_materialises_the_tph_matrix():
@@ -85,6 +97,12 @@ def test_call_surface_matches_the_reference_call_sites():
     assert sig(tph.create_raceline.create_raceline) == ["refline", "normvectors", "alpha", "stepsize_interp"]
     assert sig(tph.calc_head_curv_an.calc_head_curv_an) == ["coeffs_x", "coeffs_y", "ind_spls", "t_spls", "calc_curv",
                                                             "calc_dcurv"]
+    # velocity-profile stage, /root/reference/main_globaltraj.py:211-213, :400-421 (all keyword calls)
+    assert {"ggv", "ax_max_machines", "v_max", "kappa", "el_lengths", "closed", "filt_window", "dyn_model_exp", "drag_coeff",
+            "m_veh"} <= set(sig(tph.calc_vel_profile.calc_vel_profile))
+    assert sig(tph.calc_ax_profile.calc_ax_profile) == ["vx_profile", "el_lengths", "eq_length_output"]
+    assert sig(tph.calc_t_profile.calc_t_profile) == ["vx_profile", "el_lengths", "t_start", "ax_profile"]
+    assert sig(tph.import_veh_dyn_info.import_veh_dyn_info) == ["ggv_import_path", "ax_max_machines_import_path"]
 
 
 def test_no_cpu_fallback_without_cuda():
@@ -97,6 +115,28 @@ def test_no_cpu_fallback_without_cuda():
         tph.calc_splines.calc_splines(path=path)
     with pytest.raises(RuntimeError, match="Headings must be provided"):
         tph.calc_splines.calc_splines(path=path[:-1])
+    with pytest.raises(_lib.MinCurvLibError, match="no CPU fallback"):
+        tph.calc_vel_profile.calc_vel_profile(ggv=np.array([[0.0, 12.0, 12.0], [80.0, 12.0, 12.0]]),
+                                              ax_max_machines=np.array([[0.0, 5.0], [80.0, 5.0]]), v_max=70.0,
+                                              kappa=np.full(100, 0.01), el_lengths=np.full(100, 2.0), closed=True,
+                                              drag_coeff=0.75, m_veh=1200.0)
+    with pytest.raises(_lib.MinCurvLibError, match="no CPU fallback"):
+        tph.calc_ax_profile.calc_ax_profile(np.ones(11), np.ones(10))
+
+
+def test_import_veh_dyn_info_reads_and_checks_the_tables(tmp_path):
+    g = tmp_path / "ggv.csv"
+    m = tmp_path / "axm.csv"
+    g.write_text("# v_mps,ax_max_mps2,ay_max_mps2\n0.0,12.0,11.0\n40.0,10.0,9.5\n")
+    m.write_text("# v_mps,ax_max_machines_mps2\n0.0,5.3\n")
+    ggv, mach = tph.import_veh_dyn_info.import_veh_dyn_info(ggv_import_path=str(g), ax_max_machines_import_path=str(m))
+    assert ggv.shape == (2, 3) and mach.shape == (1, 2) and ggv[1, 2] == 9.5 and mach[0, 1] == 5.3
+    g.write_text("0.0,60.0,11.0\n")
+    with pytest.raises(RuntimeError, match="ggv seems unreasonable"):
+        tph.import_veh_dyn_info.import_veh_dyn_info(ggv_import_path=str(g))
+    g.write_text("0.0,12.0\n")
+    with pytest.raises(RuntimeError, match="three columns"):
+        tph.import_veh_dyn_info.import_veh_dyn_info(ggv_import_path=str(g))
 
 
 def test_synthetic_tracks_are_deterministic_and_well_posed():

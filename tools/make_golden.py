@@ -98,6 +98,16 @@ def spline_approximation(track, k_reg=3, s_reg=10, stepsize_prep=1.0, stepsize_r
     return np.column_stack((path, w_r_s[:-1], w_l_s[:-1]))
 
 
+def berlin_n(n: int) -> np.ndarray:
+    """The smoothed Berlin reftrack re-sampled (linear in arc length, like interp_track) to n equidistant points."""
+    rt = spline_approximation(import_track("berlin_2018"), PARS["k_reg"], PARS["s_reg"], PARS["stepsize_prep"],
+                              PARS["stepsize_reg"])
+    cl = np.vstack((rt, rt[0]))
+    s = np.insert(np.cumsum(np.sqrt(np.sum(np.diff(cl[:, :2], axis=0) ** 2, axis=1))), 0, 0.0)
+    sq = np.linspace(0.0, s[-1], n, endpoint=False)
+    return np.column_stack([np.interp(sq, s, cl[:, c]) for c in range(4)])
+
+
 def oracle_case(name: str, reftrack: np.ndarray, w_veh: float, kappa_bound: float, with_iqp: bool) -> dict:
     t0 = time.time()
     path_cl = np.vstack((reftrack[:, :2], reftrack[0, :2]))
@@ -149,10 +159,45 @@ CASES = {
     "synth500": (lambda: synth.make_track(14, 500), 2.0, 0.12, False),
     "synth500_narrow": (lambda: synth.make_track(15, 500), 5.2, 0.12, False),
     "synth1000": (lambda: synth.make_track(16, 1000), 2.0, 0.12, False),
+    # BASELINE.json configs[3] (C4) size: N = 2000 (dense oracle: ~minutes, 8000 x 8000 systems)
+    "synth2000": (lambda: synth.make_track(17, 2000), 2.0, 0.12, False),
+    # BASELINE.json configs[1] (C2): Berlin centre line re-sampled to N = 500 points, smooth width jitter,
+    # vehicle widths from the veh_width grid 1.6 ... 3.4 m
+    "berlin500_jitter_a": (lambda: synth.jitter_widths(berlin_n(500), 41), 1.6, PARS["curvlim"], False),
+    "berlin500_jitter_b": (lambda: synth.jitter_widths(berlin_n(500), 42), 3.4, PARS["curvlim"], False),
     # curvature rows |k_ref + E alpha| <= kappa_bound active at the optimum (tight kappa_bound)
     "synth160_kappa": (lambda: synth.make_track(3, 160), 2.0, 0.02, False),
     "synth333_kappa": (lambda: synth.make_track(13, 333), 2.0, 0.03, False),
 }
+
+
+def velprofile_golden():
+    """tests/golden/velprofile.npz: the reference's ggv / ax_max_machines tables and vehicle parameters
+    (/root/reference/inputs/veh_dyn_info/*.csv, /root/reference/params/racecar.ini:44-57) with what
+    oracle/tph_velprofile.py returns on the raceline kappa / el_lengths of the committed fixtures: the velocity,
+    acceleration and time profiles of the stock run, and a small lap-time matrix
+    (/root/reference/main_globaltraj.py:442-496 with a coarser grid)."""
+    from oracle import tph_velprofile as VP
+    ggv, axm = VP.import_veh_dyn_info(os.path.join(REF, "inputs", "veh_dyn_info", "ggv.csv"),
+                                      os.path.join(REF, "inputs", "veh_dyn_info", "ax_max_machines.csv"))
+    veh = dict(v_max=70.0, mass=1200.0, dragcoeff=0.75, dyn_model_exp=1.0)
+    out = dict(ggv=ggv, ax_max_machines=axm, **veh)
+    scales = np.linspace(0.3, 1.0, 4)
+    speeds = np.linspace(100.0, 150.0, 3) / 3.6
+    out.update(ltm_scales=scales, ltm_top_speeds=speeds)
+    for name in ("berlin", "handling", "modena", "synth333", "synth1000"):
+        g = np.load(os.path.join(GOLD, name + ".npz"))
+        k, el = g["rl_kappa"], g["rl_el_lengths"]
+        vx = VP.calc_vel_profile(ggv=ggv, ax_max_machines=axm, v_max=veh["v_max"], kappa=k, el_lengths=el, closed=True,
+                                 filt_window=None, dyn_model_exp=veh["dyn_model_exp"], drag_coeff=veh["dragcoeff"],
+                                 m_veh=veh["mass"])
+        ax = VP.calc_ax_profile(vx_profile=np.append(vx, vx[0]), el_lengths=el, eq_length_output=False)
+        t = VP.calc_t_profile(vx_profile=vx, ax_profile=ax, el_lengths=el)
+        out.update({name + "_vx": vx, name + "_ax": ax, name + "_t": t})
+        out[name + "_ltm"] = VP.lap_time_matrix(ggv, axm, k, el, scales, speeds, veh["dyn_model_exp"], veh["dragcoeff"],
+                                                veh["mass"])
+        print(f"  velprofile {name}: lap time {t[-1]:.3f} s, vx {vx.min():.2f}..{vx.max():.2f} m/s", flush=True)
+    np.savez_compressed(os.path.join(GOLD, "velprofile.npz"), **out)
 
 
 def main():
@@ -160,6 +205,9 @@ def main():
     ap.add_argument("--only", default="")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
+    if args.only == "velprofile":
+        velprofile_golden()
+        return
     names = [s for s in args.only.split(",") if s] or list(CASES)
     for name in names:
         build, w_veh, kb, with_iqp = CASES[name]
