@@ -155,7 +155,8 @@ def run_b200(args) -> dict:
         rl = B_.create_raceline_batch(rt_dev, nv, alpha, STEP_INTERP, n_out_max=n_out_max, with_head_curv=True)
         if timed_kernels:
             ev["raceline"][-1][1].record()
-        return dict(alpha=alpha, status=st, iters=iters, kappa=rl["kappa"], raceline=rl["raceline_interp"], n_out=rl["n_out"])
+        return dict(alpha=alpha, status=st, iters=iters, kappa=rl["kappa"], raceline=rl["raceline_interp"], n_out=rl["n_out"],
+                    el=rl["el_lengths_interp"])
 
     def sync_all():
         if world > 1:
@@ -269,11 +270,48 @@ def run_b200(args) -> dict:
                              "construction; it is bound by the serial pivot/sweep chain of one warp per instance and by that "
                              "implementation traffic, see DESIGN.md section 5"},
     }
+    if world == 1:
+        line["next_stage"] = velprofile_stage(B_, res, dev)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(n, sample=1)
     if world > 1:
         dist.destroy_process_group()
     return line if rank == 0 else None
+
+
+# ------------------------------------------------------------------------------------------------
+def velprofile_stage(B_, res: dict, dev) -> dict:
+    """Outside the timed region and not part of `value`: the stage after the path on the racelines the
+    last step produced -- the reference's lap-time matrix (15 ggv scales x 11 top speeds,
+    /root/reference/main_globaltraj.py:77-82, :442-496) for the first 512 racelines in one launch of vel_profile_kernel.
+    Reported for information; a failure here is recorded, never raised."""
+    import torch
+    try:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "velprofile.npz"))
+        scales = np.linspace(0.3, 1.0, int((1.0 - 0.3) / 0.05) + 1)
+        speeds = np.linspace(100.0 / 3.6, 150.0 / 3.6, int((150.0 - 100.0) / 5.0) + 1)
+        nb = min(512, res["kappa"].shape[0])
+        kap, el, npts = res["kappa"][:nb].contiguous(), res["el"][:nb].contiguous(), res["n_out"][:nb].contiguous()
+        args = (kap, el, g["ggv"], g["ax_max_machines"], scales, speeds, float(g["dragcoeff"]), float(g["mass"]))
+        B_.lap_time_matrix_batch(*args, n_pts=npts)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        a.record()
+        for _ in range(reps):
+            ltm = B_.lap_time_matrix_batch(*args, n_pts=npts)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        profiles = nb * scales.size * speeds.size
+        pts = float(npts.double().mean().item())
+        return {"stage": "calc_vel_profile + calc_ax_profile + calc_t_profile (lap-time matrix)", "kernel": "vel_profile_kernel",
+                "racelines": nb, "variants_per_raceline": int(scales.size * speeds.size), "profiles": profiles,
+                "points_per_profile_mean": pts, "ms_per_launch": ms, "profiles_per_s": profiles / (ms * 1e-3),
+                "lap_time_s_stock_car_mean": float(ltm[:, -1, -1].mean().item()),
+                "note": "includes the launch-side host work of lap_time_matrix_batch (table upload, status check)"}
+    except Exception as e:      # informational stage: record, do not fail the bench line
+        return {"stage": "calc_vel_profile", "error": f"{type(e).__name__}: {e}"}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -198,6 +198,19 @@ def opt_shortest_path_batch(reftrack: torch.Tensor, normvec: torch.Tensor, w_veh
     return dict(alpha=alpha, status=status, iters=iters)
 
 
+def _closed_polygon_length(pts: torch.Tensor, n_pts: Optional[torch.Tensor]) -> torch.Tensor:
+    """Length [B] of the closed polygon through the first n_pts[b] points of every row (padding ignored)."""
+    B, n_max, _ = pts.shape
+    seg = (torch.roll(pts, -1, dims=1) - pts).norm(dim=-1)
+    if n_pts is None:
+        return seg.sum(dim=1)
+    idx = torch.arange(n_max, device=pts.device).unsqueeze(0)
+    last = (n_pts.long() - 1).clamp(min=0).unsqueeze(1)
+    closing = (pts[:, 0, :] - torch.gather(pts, 1, last.unsqueeze(-1).expand(-1, 1, 2)).squeeze(1)).norm(dim=-1)
+    seg = torch.where(idx < last, seg, torch.zeros_like(seg))
+    return seg.sum(dim=1) + closing
+
+
 def create_raceline_batch(refline: torch.Tensor, normvec: torch.Tensor, alpha: torch.Tensor, stepsize_interp: float,
                           n_pts: Optional[torch.Tensor] = None, n_out_max: Optional[int] = None,
                           with_head_curv: bool = True) -> dict:
@@ -214,16 +227,7 @@ def create_raceline_batch(refline: torch.Tensor, normvec: torch.Tensor, alpha: t
     dev = refline.device
     n_pts = _npts(n_pts, B, dev)
     if n_out_max is None:
-        pts = refline[:, :, :2] + alpha.unsqueeze(-1) * normvec
-        seg = (torch.roll(pts, -1, dims=1) - pts).norm(dim=-1)
-        if n_pts is not None:      # padded tail must not count (its closing segment is replaced below)
-            idx = torch.arange(n_max, device=dev).unsqueeze(0)
-            last = (n_pts.long() - 1).clamp(min=0).unsqueeze(1)
-            closing = (pts[:, 0, :] - torch.gather(pts, 1, last.unsqueeze(-1).expand(-1, 1, 2)).squeeze(1)).norm(dim=-1)
-            seg = torch.where(idx < last, seg, torch.zeros_like(seg))
-            poly = seg.sum(dim=1) + closing
-        else:
-            poly = seg.sum(dim=1)
+        poly = _closed_polygon_length(refline[:, :, :2] + alpha.unsqueeze(-1) * normvec, n_pts)
         n_out_max = int(math.ceil(float(poly.max().item()) * 1.1 / float(stepsize_interp))) + 16
     n_out_max = int(n_out_max)
     f64 = dict(dtype=torch.float64, device=dev)
@@ -321,13 +325,21 @@ def iqp_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, ka
     h = _f64(h, "h").clone()
     B, n_max, _ = reftrack.shape
     dev = reftrack.device
-    n_cap = n_max + 64
     cur_n = (n_pts.to(device=dev, dtype=torch.int32).clone() if n_pts is not None
              else torch.full((B,), n_max, dtype=torch.int32, device=dev))
-    fin = dict(alpha=torch.zeros((B, n_cap), dtype=torch.float64, device=dev),
-               reftrack=torch.zeros((B, n_cap, 4), dtype=torch.float64, device=dev),
-               normvec=torch.zeros((B, n_cap, 2), dtype=torch.float64, device=dev),
-               n_pts=torch.zeros((B,), dtype=torch.int32, device=dev),
+    # capacity of the re-sampled tracks: the raceline is re-sampled every stepsize_interp metres, so its point count
+    # follows from its length, not from n_max (a track given at a coarser spacing grows); 5 % + 50 m of slack on the
+    # reference polygon, and the relinearisation step below grows the buffers if a track still does not fit
+    poly = float(_closed_polygon_length(reftrack[:, :, :2], cur_n).max().item())
+    n_cap = max(n_max + 64, int(math.ceil((1.05 * poly + 50.0) / float(stepsize_interp))) + 16)
+
+    def _alloc(cap):
+        return dict(alpha=torch.zeros((B, cap), dtype=torch.float64, device=dev),
+                    reftrack=torch.zeros((B, cap, 4), dtype=torch.float64, device=dev),
+                    normvec=torch.zeros((B, cap, 2), dtype=torch.float64, device=dev))
+
+    fin = _alloc(n_cap)
+    fin.update(n_pts=torch.zeros((B,), dtype=torch.int32, device=dev),
                outer_iters=torch.zeros((B,), dtype=torch.int32, device=dev),
                status=torch.zeros((B,), dtype=torch.int32, device=dev),
                curv_error_max=torch.zeros((B,), dtype=torch.float64, device=dev))
@@ -360,11 +372,18 @@ def iqp_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, ka
         active = active & ~done
         if not bool(active.any().item()):
             break
-        reftrack, normvec, cur_n = iqp_relinearise_batch(reftrack, normvec, alpha, stepsize_interp, n_pts=cur_n,
-                                                         active=active, n_max_new=n_cap)
-        too_big = active & (cur_n < 0)
-        if bool(too_big.any().item()):
-            raise RuntimeError("iqp_batch: a re-sampled raceline needs more points than the padded capacity")
+        while True:
+            rt_new, nv_new, n_new = iqp_relinearise_batch(reftrack, normvec, alpha, stepsize_interp, n_pts=cur_n,
+                                                          active=active, n_max_new=n_cap)
+            too_big = active & (n_new < 0)
+            if not bool(too_big.any().item()):
+                break
+            n_cap = int((-n_new[too_big]).max().item()) + 64        # the kernel reports -(required size)
+            grown = _alloc(n_cap)
+            for k in ("alpha", "reftrack", "normvec"):
+                grown[k][:, :fin[k].shape[1]] = fin[k]
+                fin[k] = grown[k]
+        reftrack, normvec, cur_n = rt_new, nv_new, n_new
         h = torch.ones((B, n_cap), dtype=torch.float64, device=dev)   # use_dist_scaling=False from iteration 2 on
     fin["qp_solves"] = qp_solves
     return fin
