@@ -33,7 +33,7 @@ struct VpArgs {
     double *ws;
 };
 
-__global__ void __launch_bounds__(128) vel_profile_kernel(const VpArgs a) {
+__global__ void __launch_bounds__(128, 5) vel_profile_kernel(const VpArgs a) {
     __shared__ double s_tab[5 * VP_TAB_MAX];
     double *gv = s_tab, *gax = s_tab + VP_TAB_MAX, *gay = s_tab + 2 * VP_TAB_MAX;
     double *mv = s_tab + 3 * VP_TAB_MAX, *ma = s_tab + 4 * VP_TAB_MAX;

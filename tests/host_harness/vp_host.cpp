@@ -28,4 +28,6 @@ extern "C" void vp_host_ax_t(int n, const double *vx, const double *el, const do
     ax_t_thread(n, vx, el, ax_in, t_start, ax_out, t_out);
 }
 
-extern "C" double vp_host_interp(double x, int n, const double *xp, const double *fp, double s) { return interp(x, xp, fp, n, s); }
+extern "C" double vp_host_interp(double x, int n, const double *xp, const double *fp, double s, int hint) {
+    return interp(x, xp, fp, n, s, hint);
+}

@@ -46,7 +46,7 @@ def harness(tmp_path_factory):
         lib.vp_host_ax_t.restype = None
         lib.vp_host_ax_t.argtypes = [ctypes.c_int, DP, DP, DP, ctypes.c_double, DP, DP]
         lib.vp_host_interp.restype = ctypes.c_double
-        lib.vp_host_interp.argtypes = [ctypes.c_double, ctypes.c_int, DP, DP, ctypes.c_double]
+        lib.vp_host_interp.argtypes = [ctypes.c_double, ctypes.c_int, DP, DP, ctypes.c_double, ctypes.c_int]
         out[upper] = lib
     return out
 
@@ -174,9 +174,10 @@ def test_host_interp_is_numpy_interp(harness):
         s = float(rng.choice([1.0, 0.35, 0.7]))
         xs = np.concatenate((rng.random(200) * 100.0 - 10.0, xp, [np.inf, -np.inf]))
         want = np.interp(xs, xp, fp * s)
-        got = np.array([lib.vp_host_interp(float(x), n, _p(xp), _p(fp), s) for x in xs])
-        assert np.array_equal(got, want)
-    assert np.isnan(lib.vp_host_interp(float("nan"), 3, _p(np.array([0.0, 1.0, 2.0])), _p(np.ones(3)), 1.0))
+        for hint in (0, max(n - 2, 0), max(n // 2 - 1, 0)):        # the segment hint never changes the result
+            got = np.array([lib.vp_host_interp(float(x), n, _p(xp), _p(fp), s, hint) for x in xs])
+            assert np.array_equal(got, want)
+    assert np.isnan(lib.vp_host_interp(float("nan"), 3, _p(np.array([0.0, 1.0, 2.0])), _p(np.ones(3)), 1.0, 0))
 
 
 def test_host_ax_t_profile_matches_the_oracle(harness):
