@@ -40,6 +40,13 @@ _SIGS = {
     "mc_vel_profile_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _c_dbl, _c_int, _vp, _c_int, _vp,
                                       _c_dbl, _c_dbl, _c_dbl, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mc_calc_ax_t_profile_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _c_int, _vp, _vp, _c_dbl, _vp, _vp, _vp]),
+    "mc_interp_track_workspace_bytes": (_sz, [_c_int, _c_int]),
+    "mc_interp_track_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _c_int, _vp, _c_dbl, _c_int, _c_dbl, _c_int, _vp, _vp, _vp,
+                                       _sz, _vp]),
+    "mc_min_bound_dists_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _c_int, _vp, _vp, _c_int, _c_dbl,
+                                          _c_dbl, _vp, _vp]),
+    "mc_traj_extrema_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_dbl, _c_dbl, _vp, _vp]),
+    "mc_assemble_trajectory_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp]),
     "mc_debug_read_profile": (_c_int, [_vp, _c_int]),
 }
 

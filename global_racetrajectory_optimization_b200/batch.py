@@ -512,3 +512,141 @@ def calc_ax_t_profile_batch(vx: torch.Tensor, el_lengths: torch.Tensor, ax_in: O
                                         _ptr(ax_in), float(t_start), _ptr(ax_out), _ptr(t_out), _stream())
     _lib.check(rc, "mc_calc_ax_t_profile_batch")
     return ax_out, t_out
+
+
+# ------------------------------------------------------------------------------------------------
+# trajectory back end: the reference's in-tree helpers interp_track, calc_min_bound_dists,
+# check_traj and the trajectory assembly of main_globaltraj.py:501-512, batched
+# ------------------------------------------------------------------------------------------------
+def interp_track_batch(pts: torch.Tensor, stepsize_approx: float = 1.0, n_pts: Optional[torch.Tensor] = None,
+                       normvec: Optional[torch.Tensor] = None, normal_sign: float = 1.0, width_col: int = 2,
+                       n_out_max: Optional[int] = None):
+    """Batched helper_funcs_glob.src.interp_track.interp_track (/root/reference/helper_funcs_glob/src/interp_track.py).
+
+    pts: [B, n_max, 2 or 4].  With ``normvec`` the re-sampled polyline is pts.xy + normal_sign * normvec * pts[..., width_col]
+    (the track boundaries of check_traj.py:50-61).  Returns (out [B, n_out_max, 4], n_out [B])."""
+    _require_cuda()
+    lib = _lib.load()
+    pts = _f64(pts, "pts")
+    B, n_max, stride = pts.shape
+    dev = pts.device
+    n_pts = _npts(n_pts, B, dev)
+    if normvec is not None:
+        normvec = _f64(normvec, "normvec")
+        if normvec.shape != (B, n_max, 2) or stride != 4:
+            raise ValueError("normvec needs a [B, n_max, 4] track and must be [B, n_max, 2]")
+    if n_out_max is None:
+        line = pts[:, :, :2] if normvec is None else \
+            pts[:, :, :2] + float(normal_sign) * normvec * pts[:, :, int(width_col)].unsqueeze(-1)
+        n_out_max = int(math.ceil(float(_closed_polygon_length(line, n_pts).max().item()) / float(stepsize_approx))) + 8
+    ws = _workspace("interp_track", lib.mc_interp_track_workspace_bytes(B, n_max), dev)
+    while True:
+        out = torch.zeros((B, int(n_out_max), 4), dtype=torch.float64, device=dev)
+        n_out = torch.zeros((B,), dtype=torch.int32, device=dev)
+        rc = lib.mc_interp_track_batch(B, n_max, _ptr(n_pts), _ptr(pts), stride, _ptr(normvec), float(normal_sign),
+                                       int(width_col), float(stepsize_approx), int(n_out_max), _ptr(out), _ptr(n_out),
+                                       _ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, "mc_interp_track_batch")
+        need = int((-n_out).max().item())
+        if need <= 0:
+            return out, n_out
+        n_out_max = need + 8
+
+
+def min_bound_dists_batch(xy: torch.Tensor, psi: torch.Tensor, bound1: torch.Tensor, bound2: torch.Tensor,
+                          length_veh: float, width_veh: float, n_traj: Optional[torch.Tensor] = None,
+                          nb1: Optional[torch.Tensor] = None, nb2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Batched helper_funcs_glob.src.calc_min_bound_dists.calc_min_bound_dists: [B, n_traj_max] minimum distances of
+    the vehicle corners to the boundary points (bound1/bound2: [B, nb_max, >= 2], x and y first)."""
+    _require_cuda()
+    lib = _lib.load()
+    xy, psi, bound1, bound2 = _f64(xy, "xy"), _f64(psi, "psi"), _f64(bound1, "bound1"), _f64(bound2, "bound2")
+    B, n_traj_max, _ = xy.shape
+    if bound1.shape[2] != bound2.shape[2]:
+        raise ValueError("bound1 and bound2 must have the same row layout")
+    dev = xy.device
+    out = torch.zeros((B, n_traj_max), dtype=torch.float64, device=dev)
+    rc = lib.mc_min_bound_dists_batch(B, n_traj_max, _ptr(_npts(n_traj, B, dev)), _ptr(xy), _ptr(psi), int(bound1.shape[1]),
+                                      _ptr(_npts(nb1, B, dev)), _ptr(bound1), int(bound2.shape[1]), _ptr(_npts(nb2, B, dev)),
+                                      _ptr(bound2), int(bound1.shape[2]), float(length_veh), float(width_veh), _ptr(out),
+                                      _stream())
+    _lib.check(rc, "mc_min_bound_dists_batch")
+    return out
+
+
+EXTREMA = ("min_dist", "kappa_abs_max", "ay_max", "ax_wo_drag_max", "ax_wo_drag_min", "a_tot_max", "vx_max", "n_points")
+
+
+def traj_extrema_batch(kappa: torch.Tensor, vx: torch.Tensor, ax: torch.Tensor, dragcoeff: float, mass_veh: float,
+                       min_dists: Optional[torch.Tensor] = None, n_traj: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[B, 8] extrema per trajectory, columns as in EXTREMA (min_dist = inf without min_dists)."""
+    _require_cuda()
+    lib = _lib.load()
+    kappa, vx, ax = _f64(kappa, "kappa"), _f64(vx, "vx"), _f64(ax, "ax")
+    B, n_max = kappa.shape
+    dev = kappa.device
+    if min_dists is not None:
+        min_dists = _f64(min_dists, "min_dists")
+    ext = torch.zeros((B, 8), dtype=torch.float64, device=dev)
+    rc = lib.mc_traj_extrema_batch(B, n_max, _ptr(_npts(n_traj, B, dev)), _ptr(kappa), _ptr(vx), _ptr(ax), _ptr(min_dists),
+                                   float(dragcoeff), float(mass_veh), _ptr(ext), _stream())
+    _lib.check(rc, "mc_traj_extrema_batch")
+    return ext
+
+
+def check_traj_batch(reftrack: torch.Tensor, normvec: torch.Tensor, xy: torch.Tensor, psi: torch.Tensor,
+                     kappa: torch.Tensor, vx: torch.Tensor, ax: torch.Tensor, length_veh: float, width_veh: float,
+                     dragcoeff: float, mass_veh: float, n_pts: Optional[torch.Tensor] = None,
+                     n_traj: Optional[torch.Tensor] = None, bound_stepsize: float = 1.0) -> dict:
+    """The quantities helper_funcs_glob.src.check_traj.check_traj tests, for a batch of trajectories: boundaries
+    re-sampled every ``bound_stepsize`` metres, minimum distance of the vehicle corners to them for every trajectory
+    point (against ALL boundary points -- the reference passes only the first point of each boundary, check_traj.py:58-61,
+    which the single-track mirror reproduces), and the extrema of curvature, accelerations and speed.
+    Returns dict(min_dists [B, n_traj_max], bound_r/bound_l [B, nb, 4] with nb_r/nb_l [B], and one [B] tensor per name
+    in EXTREMA)."""
+    _require_cuda()
+    kappa = _f64(kappa, "kappa")
+    B = kappa.shape[0]
+    n_traj = _npts(n_traj, B, kappa.device)
+    br, nbr = interp_track_batch(reftrack, bound_stepsize, n_pts=n_pts, normvec=normvec, normal_sign=1.0, width_col=2)
+    bl, nbl = interp_track_batch(reftrack, bound_stepsize, n_pts=n_pts, normvec=normvec, normal_sign=-1.0, width_col=3)
+    md = min_bound_dists_batch(xy, psi, br, bl, length_veh, width_veh, n_traj=n_traj, nb1=nbr, nb2=nbl)
+    ext = traj_extrema_batch(kappa, vx, ax, dragcoeff, mass_veh, min_dists=md, n_traj=n_traj)
+    out = dict(min_dists=md, bound_r=br, bound_l=bl, nb_r=nbr, nb_l=nbl)
+    out.update({name: ext[:, i] for i, name in enumerate(EXTREMA)})
+    return out
+
+
+def check_traj_flags(chk: dict, ggv, ax_max_machines, v_max: float, curvlim: float, min_dist_warn: float = 1.0) -> dict:
+    """The comparisons of check_traj.py:74-139 as boolean [B] tensors (True = the reference would print the warning)."""
+    import numpy as _np
+    f = dict(min_dist=chk["min_dist"] < min_dist_warn, curvature=chk["kappa_abs_max"] > curvlim,
+             v_max=chk["vx_max"] > v_max + 0.1)
+    if ggv is not None:
+        g = _np.asarray(ggv, dtype=float)
+        f.update(ay=chk["ay_max"] > float(g[:, 2].max()) + 0.1, ax_pos=chk["ax_wo_drag_max"] > float(g[:, 1].max()) + 0.1,
+                 ax_neg=chk["ax_wo_drag_min"] < float((-g[:, 1]).min()) - 0.1, a_tot=chk["a_tot_max"] > float(g[:, 1:].max()) + 0.1)
+    if ax_max_machines is not None:
+        m = _np.asarray(ax_max_machines, dtype=float)
+        f["ax_machines"] = chk["ax_wo_drag_max"] > float(m[:, 1].max()) + 0.1
+    return f
+
+
+def assemble_trajectory_batch(s: torch.Tensor, xy: torch.Tensor, psi: torch.Tensor, kappa: torch.Tensor, vx: torch.Tensor,
+                              ax: torch.Tensor, spline_lengths: torch.Tensor, n_traj: Optional[torch.Tensor] = None,
+                              n_spl: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """trajectory_opt / traj_race_cl of /root/reference/main_globaltraj.py:501-512 for a batch: [B, n_max + 1, 7] rows
+    [s, x, y, psi, kappa, vx, ax]; row n_traj[b] closes the lap with s = sum(spline_lengths[b])."""
+    _require_cuda()
+    lib = _lib.load()
+    s, xy, psi, kappa, vx, ax = (_f64(t, nm) for t, nm in ((s, "s"), (xy, "xy"), (psi, "psi"), (kappa, "kappa"), (vx, "vx"),
+                                                          (ax, "ax")))
+    spline_lengths = _f64(spline_lengths, "spline_lengths")
+    B, n_max = s.shape
+    dev = s.device
+    traj = torch.zeros((B, n_max + 1, 7), dtype=torch.float64, device=dev)
+    rc = lib.mc_assemble_trajectory_batch(B, n_max, _ptr(_npts(n_traj, B, dev)), _ptr(s), _ptr(xy), _ptr(psi), _ptr(kappa),
+                                          _ptr(vx), _ptr(ax), int(spline_lengths.shape[1]), _ptr(_npts(n_spl, B, dev)),
+                                          _ptr(spline_lengths), _ptr(traj), _stream())
+    _lib.check(rc, "mc_assemble_trajectory_batch")
+    return traj

@@ -39,6 +39,15 @@ int launch_vel_profile(int, int, int, const int32_t *, const double *, const dou
                        double *, double *, double *, double *, int32_t *, double *, cudaStream_t);
 void launch_ax_t_profile(int, int, const int32_t *, const double *, int, const double *, const double *, double, double *,
                          double *, cudaStream_t);
+size_t interp_track_ws_doubles(int n_max);
+void launch_interp_track(int, int, const int32_t *, const double *, int, const double *, double, int, double, int, double *,
+                         int32_t *, double *, cudaStream_t);
+void launch_min_bound_dists(int, int, const int32_t *, const double *, const double *, int, const int32_t *, const double *,
+                            int, const int32_t *, const double *, int, double, double, double *, cudaStream_t);
+void launch_traj_extrema(int, int, const int32_t *, const double *, const double *, const double *, const double *, double,
+                         double, double *, cudaStream_t);
+void launch_assemble_trajectory(int, int, const int32_t *, const double *, const double *, const double *, const double *,
+                                const double *, const double *, int, const int32_t *, const double *, double *, cudaStream_t);
 }  // namespace mc
 
 static thread_local char g_err[256] = "";
@@ -355,6 +364,56 @@ int mc_calc_ax_t_profile_batch(int P, int n_max, const int32_t *n_pts, const dou
         return bad("mc_calc_ax_t_profile_batch: bad argument");
     mc::launch_ax_t_profile(P, n_max, n_pts, vx, vx_pitch, el_lengths, ax_in, t_start, ax_out, t_out, (cudaStream_t)stream);
     return check_cuda("ax_t_profile_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t mc_interp_track_workspace_bytes(int B, int n_max) {
+    if (B <= 0 || n_max < 2) return 0;
+    return align256((size_t)B * mc::interp_track_ws_doubles(n_max) * sizeof(double));
+}
+
+int mc_interp_track_batch(int B, int n_max, const int32_t *n_pts, const double *pts, int stride, const double *normvec,
+                          double normal_sign, int width_col, double stepsize_approx, int n_out_max, double *out,
+                          int32_t *n_out, void *workspace, size_t workspace_bytes, void *stream) {
+    if (B <= 0 || n_max < 2 || !pts || (stride != 2 && stride != 4) || !(stepsize_approx > 0.0) || n_out_max <= 0 || !out ||
+        !n_out || (normvec && (stride != 4 || (width_col != 2 && width_col != 3))))
+        return bad("mc_interp_track_batch: bad argument");
+    if (!workspace || workspace_bytes < mc_interp_track_workspace_bytes(B, n_max)) {
+        snprintf(g_err, sizeof(g_err), "mc_interp_track_batch: workspace too small");
+        return MC_EWORKSPACE;
+    }
+    mc::launch_interp_track(B, n_max, n_pts, pts, stride, normvec, normal_sign, normvec ? width_col : 2, stepsize_approx,
+                            n_out_max, out, n_out, (double *)workspace, (cudaStream_t)stream);
+    return check_cuda("interp_track_kernel");
+}
+
+int mc_min_bound_dists_batch(int B, int n_traj_max, const int32_t *n_traj, const double *xy, const double *psi, int nb1_max,
+                             const int32_t *nb1, const double *bound1, int nb2_max, const int32_t *nb2, const double *bound2,
+                             int bound_stride, double length_veh, double width_veh, double *min_dists, void *stream) {
+    if (B <= 0 || B > 65535 || n_traj_max <= 0 || !xy || !psi || !bound1 || !bound2 || nb1_max <= 0 || nb2_max <= 0 ||
+        bound_stride < 2 || !min_dists)
+        return bad("mc_min_bound_dists_batch: bad argument");
+    mc::launch_min_bound_dists(B, n_traj_max, n_traj, xy, psi, nb1_max, nb1, bound1, nb2_max, nb2, bound2, bound_stride,
+                               length_veh, width_veh, min_dists, (cudaStream_t)stream);
+    return check_cuda("min_bound_dists_kernel");
+}
+
+int mc_traj_extrema_batch(int B, int n_max, const int32_t *n_traj, const double *kappa, const double *vx, const double *ax,
+                          const double *min_dists, double dragcoeff, double mass_veh, double *extrema, void *stream) {
+    if (B <= 0 || n_max <= 0 || !kappa || !vx || !ax || !extrema || !(mass_veh > 0.0))
+        return bad("mc_traj_extrema_batch: bad argument");
+    mc::launch_traj_extrema(B, n_max, n_traj, kappa, vx, ax, min_dists, dragcoeff, mass_veh, extrema, (cudaStream_t)stream);
+    return check_cuda("traj_extrema_kernel");
+}
+
+int mc_assemble_trajectory_batch(int B, int n_max, const int32_t *n_traj, const double *s, const double *xy,
+                                 const double *psi, const double *kappa, const double *vx, const double *ax, int n_spl_max,
+                                 const int32_t *n_spl, const double *spline_lengths, double *traj, void *stream) {
+    if (B <= 0 || n_max <= 0 || !s || !xy || !psi || !kappa || !vx || !ax || n_spl_max <= 0 || !spline_lengths || !traj)
+        return bad("mc_assemble_trajectory_batch: bad argument");
+    mc::launch_assemble_trajectory(B, n_max, n_traj, s, xy, psi, kappa, vx, ax, n_spl_max, n_spl, spline_lengths, traj,
+                                   (cudaStream_t)stream);
+    return check_cuda("assemble_trajectory_kernel");
 }
 
 int mc_debug_read_profile(unsigned long long *host_out16, int reset) {

@@ -198,6 +198,54 @@ int mc_calc_ax_t_profile_batch(int P, int n_max, const int32_t *n_pts, const dou
                                const double *el_lengths, const double *ax_in, double t_start,
                                double *ax_out, double *t_out, void *stream);
 
+/* -------------------------------------------------------------------------------------------------
+ * The reference's in-tree trajectory back end (these helpers live in /root/reference itself, so their fixtures are
+ * produced by the reference's own code -- tools/make_golden_ref.py).
+ *
+ * helper_funcs_glob.src.interp_track.interp_track(reftrack, stepsize_approx)
+ * -- /root/reference/helper_funcs_glob/src/interp_track.py:5-49; call sites prep_track.py:32-34 (the imported track) and
+ * check_traj.py:58-61 (the boundary polylines).  Linear re-sampling of a closed polyline at equal arc length.
+ *   pts [B][n_max][stride] (stride 2: x, y; stride 4: x, y, w_tr_right, w_tr_left), n_pts [B] or NULL
+ *   normvec [B][n_max][2] or NULL: if given, the polyline is pts.xy + normal_sign * normvec * pts[width_col]
+ *     (check_traj.py:50-51: bound_r = +normvec * w_tr_right (width_col 2), bound_l = -normvec * w_tr_left (width_col 3))
+ *     and the two width columns of the output are zero, as in check_traj.py:54-55
+ *   out [B][n_out_max][4], n_out [B]: points written (the closing point is dropped); -(required) if > n_out_max
+ * workspace: mc_interp_track_workspace_bytes(B, n_max)
+ */
+size_t mc_interp_track_workspace_bytes(int B, int n_max);
+int mc_interp_track_batch(int B, int n_max, const int32_t *n_pts, const double *pts, int stride, const double *normvec,
+                          double normal_sign, int width_col, double stepsize_approx, int n_out_max, double *out,
+                          int32_t *n_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* helper_funcs_glob.src.calc_min_bound_dists.calc_min_bound_dists(trajectory, bound1, bound2, length_veh, width_veh)
+ * -- /root/reference/helper_funcs_glob/src/calc_min_bound_dists.py:5-66, call site check_traj.py:64-68: for every
+ * trajectory point the smallest distance of the four vehicle corners (vehicle heading = psi) to any boundary point.
+ *   xy [B][n_traj_max][2], psi [B][n_traj_max], n_traj [B] or NULL
+ *   bound1/bound2 [B][nb*_max][bound_stride] (x at +0, y at +1), nb1/nb2 [B] or NULL
+ *   min_dists [B][n_traj_max]
+ */
+int mc_min_bound_dists_batch(int B, int n_traj_max, const int32_t *n_traj, const double *xy, const double *psi,
+                             int nb1_max, const int32_t *nb1, const double *bound1, int nb2_max, const int32_t *nb2,
+                             const double *bound2, int bound_stride, double length_veh, double width_veh,
+                             double *min_dists, void *stream);
+
+/* The quantities helper_funcs_glob.src.check_traj.check_traj compares with its limits
+ * (/root/reference/helper_funcs_glob/src/check_traj.py:74-139; call site main_globaltraj.py:520-532), per trajectory:
+ *   extrema [B][8] = min(min_dists) (inf if min_dists is NULL), max |kappa|, max ay = vx^2 / radius,
+ *                    max and min of ax_wo_drag = ax + vx^2 dragcoeff / mass_veh, max sqrt(ax_wo_drag^2 + ay^2), max vx,
+ *                    number of points
+ */
+int mc_traj_extrema_batch(int B, int n_max, const int32_t *n_traj, const double *kappa, const double *vx, const double *ax,
+                          const double *min_dists, double dragcoeff, double mass_veh, double *extrema, void *stream);
+
+/* trajectory_opt / traj_race_cl of /root/reference/main_globaltraj.py:501-512: rows [s, x, y, psi, kappa, vx, ax];
+ * row n_traj[b] closes the lap (copy of row 0 with s = sum(spline_lengths)).  traj [B][n_max + 1][7].
+ */
+int mc_assemble_trajectory_batch(int B, int n_max, const int32_t *n_traj, const double *s, const double *xy,
+                                 const double *psi, const double *kappa, const double *vx, const double *ax,
+                                 int n_spl_max, const int32_t *n_spl, const double *spline_lengths, double *traj,
+                                 void *stream);
+
 /* Debug aid (synchronous): reads (and optionally clears) 24 cycle counters that CTA 0 of mincurv_pdip_kernel
  * accumulates per phase -- used by tools/prof_run.py to attribute time inside the kernel. Host pointer. */
 int mc_debug_read_profile(unsigned long long *host_out24, int reset);
