@@ -650,3 +650,25 @@ def assemble_trajectory_batch(s: torch.Tensor, xy: torch.Tensor, psi: torch.Tens
                                           _ptr(spline_lengths), _ptr(traj), _stream())
     _lib.check(rc, "mc_assemble_trajectory_batch")
     return traj
+
+
+def check_normals_crossing_batch(track: torch.Tensor, normvec: torch.Tensor, horizon: int = 10,
+                                 n_pts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Batched tph.check_normals_crossing (/root/reference/helper_funcs_glob/src/prep_track.py:57-59): bool [B], True where
+    two normals at most ``horizon`` points apart cross inside the track."""
+    _require_cuda()
+    lib = _lib.load()
+    track, normvec = _f64(track, "track"), _f64(normvec, "normvec")
+    B, n_max, four = track.shape
+    if four != 4 or normvec.shape != (B, n_max, 2):
+        raise ValueError("track must be [B, n_max, 4] and normvec [B, n_max, 2]")
+    dev = track.device
+    n_pts = _npts(n_pts, B, dev)
+    smallest = n_max if n_pts is None else int(n_pts.min().item())
+    if horizon >= smallest:
+        raise RuntimeError("Horizon of %i points is too large for a track with %i points, reduce horizon!" % (horizon, smallest))
+    crossing = torch.zeros((B,), dtype=torch.int32, device=dev)
+    rc = lib.mc_check_normals_crossing_batch(B, n_max, _ptr(n_pts), _ptr(track), _ptr(normvec), int(horizon), _ptr(crossing),
+                                             _stream())
+    _lib.check(rc, "mc_check_normals_crossing_batch")
+    return crossing != 0

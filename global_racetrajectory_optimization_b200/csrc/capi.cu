@@ -48,6 +48,7 @@ void launch_traj_extrema(int, int, const int32_t *, const double *, const double
                          double, double *, cudaStream_t);
 void launch_assemble_trajectory(int, int, const int32_t *, const double *, const double *, const double *, const double *,
                                 const double *, const double *, int, const int32_t *, const double *, double *, cudaStream_t);
+void launch_normals_crossing(int, int, const int32_t *, const double *, const double *, int, int32_t *, cudaStream_t);
 }  // namespace mc
 
 static thread_local char g_err[256] = "";
@@ -414,6 +415,14 @@ int mc_assemble_trajectory_batch(int B, int n_max, const int32_t *n_traj, const 
     mc::launch_assemble_trajectory(B, n_max, n_traj, s, xy, psi, kappa, vx, ax, n_spl_max, n_spl, spline_lengths, traj,
                                    (cudaStream_t)stream);
     return check_cuda("assemble_trajectory_kernel");
+}
+
+int mc_check_normals_crossing_batch(int B, int n_max, const int32_t *n_pts, const double *track, const double *normvec,
+                                    int horizon, int32_t *crossing, void *stream) {
+    if (B <= 0 || B > 65535 || n_max < 3 || !track || !normvec || horizon < 1 || !crossing)
+        return bad("mc_check_normals_crossing_batch: bad argument");
+    mc::launch_normals_crossing(B, n_max, n_pts, track, normvec, horizon, crossing, (cudaStream_t)stream);
+    return check_cuda("normals_crossing_kernel");
 }
 
 int mc_debug_read_profile(unsigned long long *host_out16, int reset) {

@@ -205,4 +205,23 @@ void launch_assemble_trajectory(int B, int n_max, const int32_t *n_traj, const d
                                                       spline_lengths, traj);
 }
 
+// ---- tph.check_normals_crossing (prep_track.py:57-59) -------------------------------------------------------------
+// crossing[b] = 1 if any two normals within `horizon` points of each other cross inside the track (0 otherwise)
+__global__ void __launch_bounds__(128) normals_crossing_kernel(int n_max, const int32_t *n_pts, const double *track,
+                                                               const double *normvec, int horizon, int32_t *crossing) {
+    const int b = blockIdx.y;
+    const int n = n_pts ? n_pts[b] : n_max;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n <= horizon || n > n_max || i >= n) return;
+    if (tc::normals_cross_point(i, n, horizon, track + (size_t)b * n_max * 4, normvec + (size_t)b * n_max * 2))
+        atomicOr(crossing + b, 1);
+}
+
+void launch_normals_crossing(int B, int n_max, const int32_t *n_pts, const double *track, const double *normvec, int horizon,
+                             int32_t *crossing, cudaStream_t stream) {
+    cudaMemsetAsync(crossing, 0, (size_t)B * sizeof(int32_t), stream);
+    dim3 grid((n_max + 127) / 128, B);
+    normals_crossing_kernel<<<grid, 128, 0, stream>>>(n_max, n_pts, track, normvec, horizon, crossing);
+}
+
 }  // namespace mc

@@ -11,6 +11,7 @@
     calc_ax_profile    main_globaltraj.py:413-416, :482-485
     calc_t_profile     main_globaltraj.py:419-421, :488-490
     import_veh_dyn_info main_globaltraj.py:211-213           (host-side CSV reader, no compute)
+    check_normals_crossing prep_track.py:57-59               
 
 numpy in / numpy out; every call runs the CUDA kernels through the C-ABI with a batch of one
 (no CPU fallback: without the extension or a GPU these functions raise)."""
@@ -253,3 +254,17 @@ def calc_t_profile(vx_profile: np.ndarray, el_lengths: np.ndarray, t_start: floa
         ax_in = np.asarray(ax_profile, dtype=np.float64)[:n]
         _, t = _b.calc_ax_t_profile_batch(_up(vx_profile[:n]), _up(el_lengths), ax_in=_up(ax_in), t_start=float(t_start))
     return t[0].cpu().numpy()
+
+
+def check_normals_crossing(track: np.ndarray, normvec_normalized: np.ndarray, horizon: int = 10) -> bool:
+    """tph.check_normals_crossing.check_normals_crossing -> True if normals cross inside the track."""
+    track = np.asarray(track, dtype=np.float64)
+    normvec_normalized = np.asarray(normvec_normalized, dtype=np.float64)
+    no_points = track.shape[0]
+    if horizon >= no_points:
+        raise RuntimeError("Horizon of %i points is too large for a track with %i points, reduce horizon!"
+                           % (horizon, no_points))
+    elif horizon >= no_points / 2:
+        print("WARNING: Horizon of %i points makes no sense for a track with %i points, reduce horizon!"
+              % (horizon, no_points))
+    return bool(_b.check_normals_crossing_batch(_up(track), _up(normvec_normalized), int(horizon))[0].item())

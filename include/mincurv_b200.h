@@ -246,6 +246,15 @@ int mc_assemble_trajectory_batch(int B, int n_max, const int32_t *n_traj, const 
                                  int n_spl_max, const int32_t *n_spl, const double *spline_lengths, double *traj,
                                  void *stream);
 
+/* tph.check_normals_crossing.check_normals_crossing(track, normvec_normalized, horizon)
+ * -- call site /root/reference/helper_funcs_glob/src/prep_track.py:57-59: do normals of points at most `horizon` apart
+ * cross inside the track (which would make the QP's parametrisation ambiguous)?
+ *   track [B][n_max][4] (x, y, w_tr_right, w_tr_left), normvec [B][n_max][2], crossing [B] (int32): 1 = crossing found
+ *   tracks with n_pts[b] <= horizon are left at 0 (tph raises for them; the Python surface does too)
+ */
+int mc_check_normals_crossing_batch(int B, int n_max, const int32_t *n_pts, const double *track, const double *normvec,
+                                    int horizon, int32_t *crossing, void *stream);
+
 /* Debug aid (synchronous): reads (and optionally clears) 24 cycle counters that CTA 0 of mincurv_pdip_kernel
  * accumulates per phase -- used by tools/prof_run.py to attribute time inside the kernel. Host pointer. */
 int mc_debug_read_profile(unsigned long long *host_out24, int reset);

@@ -69,3 +69,10 @@ extern "C" void tc_host_extrema(int n, const double *kappa, const double *vx, co
     }
     e[0] = mn_d; e[1] = mx_k; e[2] = mx_ay; e[3] = mx_ax; e[4] = mn_ax; e[5] = mx_at; e[6] = mx_v; e[7] = (double)n;
 }
+
+// normals_crossing_kernel, one track
+extern "C" int tc_host_normals_crossing(int n, const double *track, const double *nrm, int horizon) {
+    for (int i = 0; i < n; ++i)
+        if (normals_cross_point(i, n, horizon, track, nrm)) return 1;
+    return 0;
+}

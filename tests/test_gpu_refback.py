@@ -125,3 +125,29 @@ def test_assemble_trajectory_matches_main_globaltraj(golden):
         assert np.array_equal(got[:-1], want[:-1]) and np.array_equal(got[-1, 1:], want[-1, 1:])
         assert abs(got[-1, 0] - want[-1, 0]) <= 1e-12 * want[-1, 0]              # sum(spline_lengths): summation order
         assert np.all(out[i, want.shape[0]:].cpu().numpy() == 0.0)
+
+
+def test_check_normals_crossing_batch_vs_oracle(golden):
+    """tph.check_normals_crossing (prep_track.py:57-59; tph restatement, parity unpinned) on widened fixtures."""
+    import global_racetrajectory_optimization_b200 as tph
+    from oracle import tph_prep
+    dev = torch.device("cuda")
+    gs = [golden(n) for n in NAMES]
+    scales = (1.0, 2.0, 3.0, 4.0)
+    rows, nvs, want = [], [], []
+    for g in gs:
+        for sc in scales:
+            rt = g["reftrack"].copy()
+            rt[:, 2:] *= sc
+            rows.append(rt)
+            nvs.append(g["normvec"])
+            want.append(tph_prep.check_normals_crossing(rt, g["normvec"], 10))
+    rt = torch.tensor(_pad(rows), device=dev)
+    nv = torch.tensor(_pad(nvs), device=dev)
+    npts = torch.tensor([r.shape[0] for r in rows], dtype=torch.int32, device=dev)
+    got = B_.check_normals_crossing_batch(rt, nv, 10, n_pts=npts).cpu().tolist()
+    assert got == want and any(want) and not all(want)
+    assert tph.check_normals_crossing.check_normals_crossing(track=rows[0], normvec_normalized=nvs[0], horizon=10) is False
+    assert tph.check_normals_crossing.check_normals_crossing(track=rows[3], normvec_normalized=nvs[3], horizon=10) is True
+    with pytest.raises(RuntimeError, match="too large"):
+        tph.check_normals_crossing.check_normals_crossing(track=rows[0][:8], normvec_normalized=nvs[0][:8], horizon=10)

@@ -103,6 +103,17 @@ def test_call_surface_matches_the_reference_call_sites():
     assert sig(tph.calc_ax_profile.calc_ax_profile) == ["vx_profile", "el_lengths", "eq_length_output"]
     assert sig(tph.calc_t_profile.calc_t_profile) == ["vx_profile", "el_lengths", "t_start", "ax_profile"]
     assert sig(tph.import_veh_dyn_info.import_veh_dyn_info) == ["ggv_import_path", "ax_max_machines_import_path"]
+    assert sig(tph.check_normals_crossing.check_normals_crossing) == ["track", "normvec_normalized", "horizon"]
+    # the reference's in-tree back end, main_globaltraj.py:193-195, :520-553
+    hf = tph.helper_funcs_glob.src
+    assert sig(hf.import_track.import_track) == ["file_path", "imp_opts", "width_veh"]
+    assert sig(hf.interp_track.interp_track) == ["reftrack", "stepsize_approx"]
+    assert sig(hf.calc_min_bound_dists.calc_min_bound_dists) == ["trajectory", "bound1", "bound2", "length_veh", "width_veh"]
+    assert sig(hf.check_traj.check_traj) == ["reftrack", "reftrack_normvec_normalized", "trajectory", "ggv", "ax_max_machines",
+                                             "v_max", "length_veh", "width_veh", "debug", "dragcoeff", "mass_veh", "curvlim"]
+    assert sig(hf.export_traj_race.export_traj_race) == ["file_paths", "traj_race"]
+    assert sig(hf.export_traj_ltpl.export_traj_ltpl) == ["file_paths", "spline_lengths_opt", "trajectory_opt", "reftrack",
+                                                         "normvec_normalized", "alpha_opt"]
 
 
 def test_no_cpu_fallback_without_cuda():

@@ -41,6 +41,8 @@ def tc(tmp_path_factory):
     lib.tc_host_min_bound_dists.restype = None
     lib.tc_host_min_bound_dists.argtypes = [ctypes.c_int, DP, DP, ctypes.c_int, DP, ctypes.c_int, DP, ctypes.c_int,
                                             ctypes.c_double, ctypes.c_double, DP]
+    lib.tc_host_normals_crossing.restype = ctypes.c_int
+    lib.tc_host_normals_crossing.argtypes = [ctypes.c_int, DP, DP, ctypes.c_int]
     lib.tc_host_extrema.restype = None
     lib.tc_host_extrema.argtypes = [ctypes.c_int, DP, DP, DP, DP, ctypes.c_double, ctypes.c_double, DP]
     return lib
@@ -130,3 +132,23 @@ def test_exports_are_byte_identical_to_the_reference(golden, tmp_path, name):
     fp2 = dict(traj_race_export=str(tmp_path / "race2.csv"))                       # no ggv file: SHA1 of an empty buffer
     hf.src.export_traj_race.export_traj_race(file_paths=fp2, traj_race=r["traj_race_cl"][:3])
     assert open(fp2["traj_race_export"]).read().split("\n", 1)[1] == str(r["traj_race_export_noggv"])
+
+
+def test_normals_crossing_statements_match_the_oracle(golden, tc):
+    """tph.check_normals_crossing is NOT in the reference tree (parity unpinned, oracle/tph_prep.py); the kernel's
+    statements are compared with that restatement on the fixtures with widened tracks (crossings appear from ~2x)."""
+    from oracle import tph_prep
+    positives = 0
+    for name in ("berlin", "handling", "synth333", "synth200"):
+        g = golden(name)
+        nv = np.ascontiguousarray(g["normvec"])
+        for scale in (1.0, 1.5, 2.0, 3.0, 4.0):
+            for horizon in (3, 10, 25):
+                rt = np.ascontiguousarray(g["reftrack"].copy())
+                rt[:, 2:] *= scale
+                want = tph_prep.check_normals_crossing(rt, nv, horizon)
+                assert bool(tc.tc_host_normals_crossing(rt.shape[0], _p(rt), _p(nv), horizon)) == want
+                positives += want
+    assert 10 < positives < 60                                   # both outcomes are exercised
+    with pytest.raises(RuntimeError, match="too large"):
+        tph_prep.check_normals_crossing(np.zeros((8, 4)), np.zeros((8, 2)), 10)
