@@ -18,6 +18,7 @@ import torch
 
 from . import _lib
 
+_GRID_Y_MAX = 65535  # tracks per launch of the kernels that put the track index on gridDim.y
 N_MIN = 80          # smallest closed track the banded solver supports (csrc/common.cuh N_MIN)
 STATUS_TEXT = {
     0: "ok",
@@ -566,11 +567,15 @@ def min_bound_dists_batch(xy: torch.Tensor, psi: torch.Tensor, bound1: torch.Ten
         raise ValueError("bound1 and bound2 must have the same row layout")
     dev = xy.device
     out = torch.zeros((B, n_traj_max), dtype=torch.float64, device=dev)
-    rc = lib.mc_min_bound_dists_batch(B, n_traj_max, _ptr(_npts(n_traj, B, dev)), _ptr(xy), _ptr(psi), int(bound1.shape[1]),
-                                      _ptr(_npts(nb1, B, dev)), _ptr(bound1), int(bound2.shape[1]), _ptr(_npts(nb2, B, dev)),
-                                      _ptr(bound2), int(bound1.shape[2]), float(length_veh), float(width_veh), _ptr(out),
-                                      _stream())
-    _lib.check(rc, "mc_min_bound_dists_batch")
+    n_traj, nb1, nb2 = _npts(n_traj, B, dev), _npts(nb1, B, dev), _npts(nb2, B, dev)
+    sl = lambda t, s, e: _ptr(t[s:e]) if t is not None else None
+    for s in range(0, B, _GRID_Y_MAX):           # the track index is the y dimension of the launch grid
+        e = min(B, s + _GRID_Y_MAX)
+        rc = lib.mc_min_bound_dists_batch(e - s, n_traj_max, sl(n_traj, s, e), _ptr(xy[s:e]), _ptr(psi[s:e]),
+                                          int(bound1.shape[1]), sl(nb1, s, e), _ptr(bound1[s:e]), int(bound2.shape[1]),
+                                          sl(nb2, s, e), _ptr(bound2[s:e]), int(bound1.shape[2]), float(length_veh),
+                                          float(width_veh), _ptr(out[s:e]), _stream())
+        _lib.check(rc, "mc_min_bound_dists_batch")
     return out
 
 
@@ -668,7 +673,10 @@ def check_normals_crossing_batch(track: torch.Tensor, normvec: torch.Tensor, hor
     if horizon >= smallest:
         raise RuntimeError("Horizon of %i points is too large for a track with %i points, reduce horizon!" % (horizon, smallest))
     crossing = torch.zeros((B,), dtype=torch.int32, device=dev)
-    rc = lib.mc_check_normals_crossing_batch(B, n_max, _ptr(n_pts), _ptr(track), _ptr(normvec), int(horizon), _ptr(crossing),
-                                             _stream())
-    _lib.check(rc, "mc_check_normals_crossing_batch")
+    for s in range(0, B, _GRID_Y_MAX):
+        e = min(B, s + _GRID_Y_MAX)
+        rc = lib.mc_check_normals_crossing_batch(e - s, n_max, _ptr(n_pts[s:e]) if n_pts is not None else None,
+                                                 _ptr(track[s:e]), _ptr(normvec[s:e]), int(horizon), _ptr(crossing[s:e]),
+                                                 _stream())
+        _lib.check(rc, "mc_check_normals_crossing_batch")
     return crossing != 0

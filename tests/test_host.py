@@ -160,3 +160,24 @@ def test_synthetic_tracks_are_deterministic_and_well_posed():
     assert d.std() / d.mean() < 0.02                  # equidistant points
     j = synth.jitter_widths(a, 3)
     assert np.array_equal(j[:, :2], a[:, :2]) and np.abs(j[:, 2:] / a[:, 2:] - 1).max() <= 0.1 + 1e-12
+
+
+def test_default_pars_are_the_stock_racecar_ini_values():
+    """globaltraj.default_pars() against /root/reference/params/racecar.ini, parsed the way main_globaltraj.py:160-183 does
+    (configparser + json); only in the build container (the GPU box has no /root/reference)."""
+    import configparser
+    import json
+    import os
+    ini = "/root/reference/params/racecar.ini"
+    if not os.path.exists(ini):
+        pytest.skip("reference tree not present")
+    from global_racetrajectory_optimization_b200 import globaltraj
+    parser = configparser.ConfigParser()
+    assert parser.read(ini)
+    ref = {k: json.loads(parser.get("GENERAL_OPTIONS", k)) for k in ("stepsize_opts", "veh_params", "vel_calc_opts")}
+    ref["optim_opts"] = json.loads(parser.get("OPTIMIZATION_OPTIONS", "optim_opts_mincurv"))
+    assert json.loads(parser.get("OPTIMIZATION_OPTIONS", "optim_opts_shortest_path"))["width_opt"] == ref["optim_opts"]["width_opt"]
+    mine = globaltraj.default_pars()
+    for section, values in mine.items():
+        for key, val in values.items():
+            assert ref[section][key] == val, (section, key)
