@@ -1,0 +1,116 @@
+"""CPU tests (-m "not gpu") of the host logic above the C-ABI: every batched wrapper is run against a recording stand-in
+of libmincurv_b200.so (no compute: each entry point only checks its argument count against the ctypes signature table and
+returns MC_OK), with CPU tensors in place of device buffers.  Catches arity / ordering / chunking mistakes in batch.py and
+globaltraj.py without a GPU; the numerical behaviour is covered by the -m gpu tests."""
+import numpy as np
+import pytest
+import torch
+
+from global_racetrajectory_optimization_b200 import _lib, batch as B_, globaltraj
+
+
+class FakeLib:
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        if name not in _lib._SIGS:
+            raise AttributeError(name)
+        res, args = _lib._SIGS[name]
+
+        def fn(*a):
+            assert len(a) == len(args), f"{name}: {len(a)} arguments passed, {len(args)} declared"
+            self.calls.append((name, a))
+            if name.endswith("_workspace_bytes"):
+                return 4096
+            return 0
+        return fn
+
+
+@pytest.fixture()
+def fake(monkeypatch):
+    lib = FakeLib()
+    monkeypatch.setattr(_lib, "load", lambda build_if_missing=True: lib)
+    monkeypatch.setattr(_lib, "check", lambda rc, what: None)
+    monkeypatch.setattr(B_, "_require_cuda", lambda: None)
+    monkeypatch.setattr(B_, "_f64", lambda t, name: t.contiguous())
+    monkeypatch.setattr(B_, "_stream", lambda: None)
+    monkeypatch.setattr(B_, "_chunk", lambda B, per_item, dev: max(1, B // 2))      # force the chunked paths
+    monkeypatch.setattr(B_, "_WS", {})
+    return lib
+
+
+def _names(lib):
+    return [c[0] for c in lib.calls]
+
+
+def test_every_wrapper_matches_the_signature_table(fake):
+    B, n = 5, 120
+    rt = torch.rand((B, n, 4), dtype=torch.float64) + 3.0
+    npts = torch.full((B,), n, dtype=torch.int32)
+    cx, cy, nv, h = B_.calc_splines_batch(rt, n_pts=npts)
+    res = B_.opt_min_curv_batch(rt, nv, h, 0.12, torch.full((B,), 2.0, dtype=torch.float64), n_pts=npts)
+    assert _names(fake).count("mc_mincurv_solve_batch") == 3                        # 5 tracks in chunks of 2
+    assert res["alpha"].shape == (B, n)
+    alpha = torch.zeros((B, n), dtype=torch.float64)      # (the stand-in library writes nothing: outputs are uninitialised)
+    B_.opt_shortest_path_batch(rt, nv, 2.0, n_pts=npts)
+    rl = B_.create_raceline_batch(rt, nv, alpha, 2.0, n_pts=npts)
+    B_.calc_head_curv_batch(rl["coeffs_x"], rl["coeffs_y"], rl["spline_inds"], rl["t_values"], n_eval=rl["n_out"])
+    B_.iqp_relinearise_batch(rt, nv, alpha, 3.0, n_pts=npts)
+    B_.scale_alpha_batch(alpha, 0.5)
+    ggv = np.array([[0.0, 12.0, 12.0], [80.0, 12.0, 12.0]])
+    mach = np.array([[0.0, 5.0], [80.0, 5.0]])
+    kap, el = torch.rand((B, 200), dtype=torch.float64), torch.ones((B, 200), dtype=torch.float64)
+    vp = B_.vel_profile_batch(kap, el, ggv, mach, 70.0, 0.75, 1200.0, n_pts=torch.full((B,), 200, dtype=torch.int32))
+    assert vp["vx"].shape == (B, 1, 200) and vp["t"].shape == (B, 1, 201) and _names(fake).count("mc_vel_profile_batch") == 3
+    ltm = B_.lap_time_matrix_batch(kap, el, ggv, mach, [0.5, 1.0], [30.0, 40.0, 50.0], 0.75, 1200.0)
+    assert ltm.shape == (B, 3, 2)
+    last = [c for c in fake.calls if c[0] == "mc_vel_profile_batch"][-1][1]
+    assert last[6] == 6                                                              # V = 3 top speeds x 2 ggv scales
+    B_.calc_ax_t_profile_batch(torch.rand((B, 201), dtype=torch.float64), el)
+    out, n_out = B_.interp_track_batch(rt, 1.0, n_pts=npts)
+    assert out.shape[0] == B and out.shape[2] == 4
+    chk = B_.check_traj_batch(rt, nv, torch.rand((B, 200, 2), dtype=torch.float64), kap, kap, kap, kap, 4.7, 2.0, 0.75, 1200.0,
+                              n_pts=npts)
+    assert set(B_.EXTREMA) <= set(chk) and chk["min_dists"].shape == (B, 200)
+    flags = B_.check_traj_flags(chk, ggv, mach, 70.0, 0.12)
+    assert set(flags) == {"min_dist", "curvature", "v_max", "ay", "ax_pos", "ax_neg", "a_tot", "ax_machines"}
+    B_.assemble_trajectory_batch(kap, torch.rand((B, 200, 2), dtype=torch.float64), kap, kap, kap, kap,
+                                 torch.rand((B, n), dtype=torch.float64))
+    assert B_.check_normals_crossing_batch(rt, nv, 10, n_pts=npts).shape == (B,)
+    with pytest.raises(RuntimeError, match="too large"):
+        B_.check_normals_crossing_batch(rt, nv, n, n_pts=npts)
+    used = set(_names(fake))
+    assert used >= set(_lib.EXPORTED_SYMBOLS) - {"mc_version", "mc_last_error", "mc_debug_read_profile", "mc_mincurv_setup_batch",
+                                                 "mc_mincurv_pdip_batch", "mc_mincurv_finalize_batch", "mc_mincurv_kappa_batch"}
+
+
+def test_launches_with_the_track_index_on_grid_y_are_chunked(fake, monkeypatch):
+    monkeypatch.setattr(B_, "_GRID_Y_MAX", 2)
+    B, n = 5, 100
+    rt = torch.rand((B, n, 4), dtype=torch.float64)
+    nv = torch.rand((B, n, 2), dtype=torch.float64)
+    B_.check_normals_crossing_batch(rt, nv, 10)
+    B_.min_bound_dists_batch(torch.rand((B, 50, 2), dtype=torch.float64), torch.rand((B, 50), dtype=torch.float64), rt, rt,
+                             4.7, 2.0)
+    sizes = [c[1][0] for c in fake.calls if c[0] == "mc_check_normals_crossing_batch"]
+    assert sizes == [2, 2, 1]
+    assert [c[1][0] for c in fake.calls if c[0] == "mc_min_bound_dists_batch"] == [2, 2, 1]
+
+
+@pytest.mark.parametrize("opt_type", ["mincurv", "shortest_path"])
+def test_globaltraj_batch_wires_the_stages_in_the_reference_order(fake, opt_type):
+    B, n = 3, 150
+    rt = torch.rand((B, n, 4), dtype=torch.float64) + 3.0
+    ggv = np.array([[0.0, 12.0, 12.0], [80.0, 12.0, 12.0]])
+    mach = np.array([[0.0, 5.0], [80.0, 5.0]])
+    out = globaltraj.globaltraj_batch(rt, opt_type, globaltraj.default_pars(), ggv, mach)
+    order = [nm for nm in _names(fake) if not nm.endswith("_workspace_bytes")]
+    qp = "mc_mincurv_solve_batch" if opt_type == "mincurv" else "mc_shortest_path_solve_batch"
+    want = ["mc_calc_splines_batch", qp, "mc_create_raceline_batch", "mc_vel_profile_batch", "mc_assemble_trajectory_batch",
+            "mc_interp_track_batch", "mc_min_bound_dists_batch", "mc_traj_extrema_batch"]
+    stages = [nm for k, nm in enumerate(order) if nm in want and (k == 0 or order[k - 1] != nm)]    # chunked launches collapse
+    assert stages == want
+    assert out["trajectory"].shape[2] == 7 and out["laptime"].shape == (B,) and "min_dist" in out
+    with pytest.raises(IOError):
+        globaltraj.globaltraj_batch(rt, "mintime", globaltraj.default_pars(), ggv, mach)
