@@ -1,5 +1,6 @@
 import numpy as np, sys, time
-sys.path.insert(0,'/root/repo')
+import os
+sys.path.insert(0,os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import tph_dense as T
 from global_racetrajectory_optimization_b200 import synth as S
 F_SCALE=2.0

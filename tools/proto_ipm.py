@@ -1,8 +1,10 @@
 import numpy as np, sys, time
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/tmp')
+import os
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0,ROOT); sys.path.insert(0,os.path.join(ROOT,'tools'))
 from oracle import tph_dense as T
 from global_racetrajectory_optimization_b200 import synth as S
-from proto2 import Model, dense_from_band
+from proto_banded_model import Model, dense_from_band
 
 def ipm_box(H, f, lb, ub, tol=1e-9, maxit=60, verbose=False, solve=None):
     N=len(f)
