@@ -114,3 +114,46 @@ def test_globaltraj_batch_wires_the_stages_in_the_reference_order(fake, opt_type
     assert out["trajectory"].shape[2] == 7 and out["laptime"].shape == (B,) and "min_dist" in out
     with pytest.raises(IOError):
         globaltraj.globaltraj_batch(rt, "mintime", globaltraj.default_pars(), ggv, mach)
+
+
+def test_iqp_batch_grows_its_buffers_when_a_resampled_track_does_not_fit(fake, monkeypatch):
+    """mc_iqp_relinearise_batch reports -(required points) for a track that exceeds the capacity; iqp_batch must enlarge
+    every per-track buffer and repeat the step.  The stand-in writes those counts into the (CPU) n_pts_new tensor."""
+    import ctypes
+    B, n = 2, 100
+    state = {"calls": 0, "caps": []}
+    real_getattr = FakeLib.__getattr__
+
+    def patched(self, name):
+        fn = real_getattr(self, name)
+        if name == "mc_mincurv_solve_batch":
+            def solve(*a):
+                fn(*a)
+                bq, nmax = a[0], a[1]
+                ctypes.memset(a[9].value, 0, bq * nmax * 8)                      # alpha = 0
+                ctypes.memset(a[10].value, 0, bq * 8)                            # curv_error_max = 0 (converged once iter >= iters_min)
+                ctypes.memset(a[12].value, 0, bq * 4)                            # status = 0
+                return 0
+            return solve
+        if name != "mc_iqp_relinearise_batch":
+            return fn
+
+        def relin(*a):
+            fn(*a)
+            state["calls"] += 1
+            cap = a[8]
+            state["caps"].append(cap)
+            need = -(cap + 40) if state["calls"] == 1 else cap - 5              # first answer: does not fit
+            arr = (ctypes.c_int32 * B)(*([need] * B))
+            ctypes.memmove(a[11].value, arr, 4 * B)
+            return 0
+        return relin
+    monkeypatch.setattr(FakeLib, "__getattr__", patched)
+    rt = torch.rand((B, n, 4), dtype=torch.float64) + 3.0
+    nv = torch.rand((B, n, 2), dtype=torch.float64)
+    h = torch.ones((B, n), dtype=torch.float64)
+    res = B_.iqp_batch(rt, nv, h, 0.12, 2.0, 3.0, iters_min=2, curv_error_allowed=0.01)
+    assert state["calls"] == 2 and state["caps"][1] == state["caps"][0] + 40 + 64          # grown, then accepted
+    cap = state["caps"][1]
+    assert res["alpha"].shape == (B, cap) and res["reftrack"].shape == (B, cap, 4) and res["normvec"].shape == (B, cap, 2)
+    assert res["outer_iters"].tolist() == [2, 2] and res["n_pts"].tolist() == [cap - 5, cap - 5] and res["qp_solves"] == 4
