@@ -22,6 +22,9 @@ _SIGS = {
     "mc_mincurv_workspace_bytes": (_sz, [_c_int, _c_int]),
     "mc_mincurv_solve_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _c_dbl, _c_dbl, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _sz, _vp]),
+    "mc_mincurv_solve_batch_ex": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _c_dbl, _c_dbl, _vp, _c_dbl, _vp, _vp, _vp, _vp,
+                                           _vp, _vp, _sz, _vp]),
+    "mc_mincurv_setup_batch_ex": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _c_dbl, _vp, _c_dbl, _vp, _vp, _sz, _vp]),
     "mc_mincurv_setup_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _c_dbl, _vp, _vp, _vp, _sz, _vp]),
     "mc_mincurv_pdip_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mc_mincurv_finalize_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _c_dbl, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -39,6 +42,8 @@ _SIGS = {
     "mc_vel_profile_workspace_bytes": (_sz, [_c_int, _c_int, _c_int]),
     "mc_vel_profile_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _c_dbl, _c_int, _vp, _c_int, _vp,
                                       _c_dbl, _c_dbl, _c_dbl, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mc_vel_profile_batch_ex": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _c_dbl, _c_int, _vp, _c_int, _vp,
+                                         _c_dbl, _c_dbl, _c_dbl, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mc_calc_ax_t_profile_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _c_int, _vp, _vp, _c_dbl, _vp, _vp, _vp]),
     "mc_interp_track_workspace_bytes": (_sz, [_c_int, _c_int]),
     "mc_interp_track_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _c_int, _vp, _c_dbl, _c_int, _c_dbl, _c_int, _vp, _vp, _vp,
@@ -49,6 +54,7 @@ _SIGS = {
     "mc_assemble_trajectory_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp]),
     "mc_check_normals_crossing_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp]),
     "mc_debug_read_profile": (_c_int, [_vp, _c_int]),
+    "mc_debug_factor_solve": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _sz, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

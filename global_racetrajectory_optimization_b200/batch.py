@@ -11,6 +11,7 @@ used by /root/reference/main_globaltraj.py:264-290,371-387 on top of them.
 from __future__ import annotations
 
 import ctypes
+import functools
 import math
 from typing import Optional, Union
 
@@ -29,12 +30,18 @@ STATUS_TEXT = {
     -1: "unsupported track size",
 }
 
+# The two constants of trajectory_planning_helpers that cannot be confirmed offline (include/mincurv_b200.h,
+# DESIGN.md section 2).  Run-time parameters of the C-ABI (*_ex entry points); tools/pin_against_tph.py determines them
+# from the real package when it is importable and tests/test_real_tph.py then runs with what it found.
+F_SCALE = 2.0               # tph.opt_min_curv: f = F_SCALE * E^T k_ref
+VP_DECEL_SLICE_UPPER = 1    # tph.calc_vel_profile (closed): half of the doubled lap kept after the backward pass
+
 _WS = {}
 
 # mirror of csrc/mincurv_ws.cuh (debugging / tests read intermediate results out of the workspace)
 SLAB_VECTORS = ("H DIAG DFW DBW LFW INVD TII RHOP RHOM PX PY NX NY MX MY XP YP SX SY KREF LB UB F "
                 "T0 T1 T2 T3 T4 T5 ALPHA LU LL RD RHS DX DD DLU DLL SU SL ISU ISL YPAD "
-                "S3 S4 L3 L4 KL WK EDX T3K T4K VV IH").split()
+                "S3 S4 L3 L4 KL WK EDX T3K T4K VV IH WP TP").split()
 HB_PITCH = 34
 ZB_PITCH = 108
 
@@ -48,7 +55,7 @@ def mincurv_slab_layout(n_max: int) -> dict:
     o_hb = o
     o += np_ * HB_PITCH
     o_tiles = o
-    o += (3 * nb_max + 1) * 1024
+    o += np_ * (32 + 33)
     return dict(np=np_, nb_max=nb_max, o_zb=o_zb, o_hb=o_hb, o_tiles=o_tiles, stride=(o + 15) & ~15)
 
 
@@ -66,8 +73,25 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _device_guard(fn):
+    """Run fn with the device of its first CUDA tensor argument current: the library launches on the calling thread's
+    current device and on that device's current stream."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = next((a.device for a in list(args) + list(kwargs.values()) if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if dev is None:
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def _workspace(kind: str, nbytes: int, device) -> torch.Tensor:
-    key = (kind, str(device))
+    """Scratch buffer of the library for one (kind, device, stream): calls on different streams never share slabs or the
+    work counter of the persistent solver kernels.  A buffer is allocated while its stream is current, so when a larger
+    one replaces it the caching allocator re-uses the old block in that stream's order only."""
+    dev = torch.device(device)
+    key = (kind, str(dev), int(torch.cuda.current_stream(dev).cuda_stream) if dev.type == "cuda" else 0)
     ws = _WS.get(key)
     if ws is None or ws.numel() < nbytes:
         _WS[key] = None
@@ -98,6 +122,7 @@ def _npts(n_pts, B, device):
 
 
 # ------------------------------------------------------------------------------------------------
+@_device_guard
 def calc_splines_batch(xy: torch.Tensor, n_pts: Optional[torch.Tensor] = None,
                        el_lengths: Optional[torch.Tensor] = None, use_dist_scaling: bool = True,
                        want_coeffs: bool = True):
@@ -139,11 +164,13 @@ def _chunk(B: int, per_item_bytes: int, device) -> int:
     return max(1, min(B, budget // max(per_item_bytes, 1)))
 
 
+@_device_guard
 def opt_min_curv_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, kappa_bound: float,
                        w_veh: Union[float, torch.Tensor], n_pts: Optional[torch.Tensor] = None,
-                       max_chunk: Optional[int] = None) -> dict:
+                       max_chunk: Optional[int] = None, f_scale: Optional[float] = None) -> dict:
     """Batched tph.opt_min_curv (closed tracks).  Returns a dict of device tensors:
-    alpha [B, n_max], curv_error_max [B], kappa_lin_max [B], status [B] (int32), iters [B] (int32)."""
+    alpha [B, n_max], curv_error_max [B], kappa_lin_max [B], status [B] (int32), iters [B] (int32).
+    f_scale: None = the module default F_SCALE (see there)."""
     _require_cuda()
     lib = _lib.load()
     reftrack = _f64(reftrack, "reftrack")
@@ -167,15 +194,17 @@ def opt_min_curv_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.T
     ws = _workspace("mincurv", lib.mc_mincurv_workspace_bytes(chunk, n_max), dev)
     for s in range(0, B, chunk):
         e = min(B, s + chunk)
-        rc = lib.mc_mincurv_solve_batch(e - s, n_max, _ptr(n_pts[s:e]) if n_pts is not None else None,
-                                        _ptr(reftrack[s:e]), _ptr(normvec[s:e]), _ptr(h[s:e]), float(kappa_bound),
-                                        w_scalar, _ptr(w_batch[s:e]) if w_batch is not None else None,
-                                        _ptr(alpha[s:e]), _ptr(cerr[s:e]), _ptr(kmax[s:e]), _ptr(status[s:e]),
-                                        _ptr(iters[s:e]), _ptr(ws), ws.numel(), _stream())
-        _lib.check(rc, "mc_mincurv_solve_batch")
+        rc = lib.mc_mincurv_solve_batch_ex(e - s, n_max, _ptr(n_pts[s:e]) if n_pts is not None else None,
+                                           _ptr(reftrack[s:e]), _ptr(normvec[s:e]), _ptr(h[s:e]), float(kappa_bound),
+                                           w_scalar, _ptr(w_batch[s:e]) if w_batch is not None else None,
+                                           float(F_SCALE if f_scale is None else f_scale),
+                                           _ptr(alpha[s:e]), _ptr(cerr[s:e]), _ptr(kmax[s:e]), _ptr(status[s:e]),
+                                           _ptr(iters[s:e]), _ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, "mc_mincurv_solve_batch_ex")
     return dict(alpha=alpha, curv_error_max=cerr, kappa_lin_max=kmax, status=status, iters=iters)
 
 
+@_device_guard
 def opt_shortest_path_batch(reftrack: torch.Tensor, normvec: torch.Tensor, w_veh: Union[float, torch.Tensor],
                             n_pts: Optional[torch.Tensor] = None) -> dict:
     """Batched tph.opt_shortest_path.  Returns dict(alpha, status, iters)."""
@@ -212,13 +241,15 @@ def _closed_polygon_length(pts: torch.Tensor, n_pts: Optional[torch.Tensor]) -> 
     return seg.sum(dim=1) + closing
 
 
+@_device_guard
 def create_raceline_batch(refline: torch.Tensor, normvec: torch.Tensor, alpha: torch.Tensor, stepsize_interp: float,
                           n_pts: Optional[torch.Tensor] = None, n_out_max: Optional[int] = None,
                           with_head_curv: bool = True) -> dict:
     """Batched tph.create_raceline (+ tph.calc_head_curv_an at the resampled points).
 
     refline: [B, n_max, 2] or a reftrack [B, n_max, 4].  If n_out_max is None an upper bound is derived from
-    the polygon length of the shifted line (one small device->host read)."""
+    the polygon length of the shifted line (one small device->host read) and the call is repeated with a larger one if
+    a track still does not fit; with an explicit n_out_max an overflow is reported as n_out[b] = -(points needed)."""
     _require_cuda()
     lib = _lib.load()
     refline = _f64(refline, "refline")
@@ -227,10 +258,24 @@ def create_raceline_batch(refline: torch.Tensor, normvec: torch.Tensor, alpha: t
     B, n_max, stride = refline.shape
     dev = refline.device
     n_pts = _npts(n_pts, B, dev)
-    if n_out_max is None:
+    derived = n_out_max is None
+    if derived:
         poly = _closed_polygon_length(refline[:, :, :2] + alpha.unsqueeze(-1) * normvec, n_pts)
         n_out_max = int(math.ceil(float(poly.max().item()) * 1.1 / float(stepsize_interp))) + 16
     n_out_max = int(n_out_max)
+    while True:
+        out = _create_raceline_once(lib, refline, normvec, alpha, stepsize_interp, n_pts, n_out_max, with_head_curv)
+        if not derived:           # the caller fixed the capacity: an overflow is reported as n_out[b] = -(points needed)
+            return out
+        need = int((-out["n_out"]).max().item())
+        if need <= 0:
+            return out
+        n_out_max = need + 16     # (the spline is longer than 1.1 x its polygon: re-run with what the kernel asked for)
+
+
+def _create_raceline_once(lib, refline, normvec, alpha, stepsize_interp, n_pts, n_out_max, with_head_curv):
+    B, n_max, stride = refline.shape
+    dev = refline.device
     f64 = dict(dtype=torch.float64, device=dev)
     out = dict(
         coeffs_x=torch.zeros((B, n_max, 4), **f64), coeffs_y=torch.zeros((B, n_max, 4), **f64),
@@ -253,6 +298,7 @@ def create_raceline_batch(refline: torch.Tensor, normvec: torch.Tensor, alpha: t
     return out
 
 
+@_device_guard
 def calc_head_curv_batch(coeffs_x: torch.Tensor, coeffs_y: torch.Tensor, ind_spls: torch.Tensor, t_spls: torch.Tensor,
                          n_eval: Optional[torch.Tensor] = None, calc_curv: bool = True, calc_dcurv: bool = False):
     _require_cuda()
@@ -276,6 +322,7 @@ def calc_head_curv_batch(coeffs_x: torch.Tensor, coeffs_y: torch.Tensor, ind_spl
     return psi, kappa, dkappa
 
 
+@_device_guard
 def iqp_relinearise_batch(reftrack, normvec, alpha, stepsize_interp, n_pts=None, active=None, n_max_new=None):
     """One re-linearisation step of tph.iqp_handler for every (active) track: returns
     (reftrack_new [B, n_max_new, 4], normvec_new [B, n_max_new, 2], n_pts_new [B])."""
@@ -302,6 +349,7 @@ def iqp_relinearise_batch(reftrack, normvec, alpha, stepsize_interp, n_pts=None,
     return rnew, nnew, npn
 
 
+@_device_guard
 def scale_alpha_batch(alpha: torch.Tensor, scale: Union[float, torch.Tensor]) -> None:
     lib = _lib.load()
     B, n_max = alpha.shape
@@ -310,6 +358,7 @@ def scale_alpha_batch(alpha: torch.Tensor, scale: Union[float, torch.Tensor]) ->
     _lib.check(rc, "mc_scale_alpha_batch")
 
 
+@_device_guard
 def iqp_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, kappa_bound: float,
               w_veh: Union[float, torch.Tensor], stepsize_interp: float, iters_min: int = 3,
               curv_error_allowed: float = 0.01, n_pts: Optional[torch.Tensor] = None, max_iters: int = 50,
@@ -403,10 +452,12 @@ def _table(t, cols: int, name: str, dev) -> torch.Tensor:
     return t
 
 
+@_device_guard
 def vel_profile_batch(kappa: torch.Tensor, el_lengths: torch.Tensor, ggv, ax_max_machines, v_max,
                       drag_coeff: float, m_veh: float, dyn_model_exp: float = 1.0, filt_window: Optional[int] = None,
                       mu: Optional[torch.Tensor] = None, n_pts: Optional[torch.Tensor] = None,
-                      ggv_scales=None, want_profiles: bool = True, max_chunk: Optional[int] = None) -> dict:
+                      ggv_scales=None, want_profiles: bool = True, max_chunk: Optional[int] = None,
+                      decel_slice_upper: Optional[int] = None) -> dict:
     """Batched tph.calc_vel_profile (closed, ggv branch) + calc_ax_profile + calc_t_profile.
 
     kappa, el_lengths: [B, n_max] device tensors (n_pts[b] valid entries), e.g. the ``kappa`` /
@@ -464,14 +515,15 @@ def vel_profile_batch(kappa: torch.Tensor, el_lengths: torch.Tensor, ggv, ax_max
     ws = _workspace("velprofile", lib.mc_vel_profile_workspace_bytes(chunk, V, n_max), dev)
     for s in range(0, B, chunk):
         e = min(B, s + chunk)
-        rc = lib.mc_vel_profile_batch(e - s, n_max, _ptr(n_pts[s:e]) if n_pts is not None else None, _ptr(kappa[s:e]),
-                                      _ptr(el_lengths[s:e]), _ptr(mu[s:e]) if mu is not None else None, V, _ptr(scale_t),
-                                      _ptr(vmax_t), v_scalar, int(ggv_t.shape[0]), _ptr(ggv_t), int(mach_t.shape[0]),
-                                      _ptr(mach_t), float(dyn_model_exp), float(drag_coeff), float(m_veh), fw,
-                                      _ptr(vx[s:e]) if vx is not None else None, _ptr(ax[s:e]) if ax is not None else None,
-                                      _ptr(t[s:e]) if t is not None else None, _ptr(laptime[s:e]), _ptr(status[s:e]),
-                                      _ptr(ws), ws.numel(), _stream())
-        _lib.check(rc, "mc_vel_profile_batch")
+        rc = lib.mc_vel_profile_batch_ex(e - s, n_max, _ptr(n_pts[s:e]) if n_pts is not None else None, _ptr(kappa[s:e]),
+                                         _ptr(el_lengths[s:e]), _ptr(mu[s:e]) if mu is not None else None, V, _ptr(scale_t),
+                                         _ptr(vmax_t), v_scalar, int(ggv_t.shape[0]), _ptr(ggv_t), int(mach_t.shape[0]),
+                                         _ptr(mach_t), float(dyn_model_exp), float(drag_coeff), float(m_veh), fw,
+                                         int(VP_DECEL_SLICE_UPPER if decel_slice_upper is None else decel_slice_upper),
+                                         _ptr(vx[s:e]) if vx is not None else None, _ptr(ax[s:e]) if ax is not None else None,
+                                         _ptr(t[s:e]) if t is not None else None, _ptr(laptime[s:e]), _ptr(status[s:e]),
+                                         _ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, "mc_vel_profile_batch_ex")
     out = dict(laptime=laptime, status=status)
     if want_profiles:
         out.update(vx=vx, ax=ax, t=t)
@@ -495,6 +547,7 @@ def lap_time_matrix_batch(kappa: torch.Tensor, el_lengths: torch.Tensor, ggv, ax
     return res["laptime"].reshape(kappa.shape[0], ts.numel(), gs.numel())
 
 
+@_device_guard
 def calc_ax_t_profile_batch(vx: torch.Tensor, el_lengths: torch.Tensor, ax_in: Optional[torch.Tensor] = None,
                             t_start: float = 0.0, n_pts: Optional[torch.Tensor] = None, want_t: bool = True):
     """Stand-alone tph.calc_ax_profile (ax_in None: vx holds n + 1 values per row) / tph.calc_t_profile.
@@ -519,6 +572,7 @@ def calc_ax_t_profile_batch(vx: torch.Tensor, el_lengths: torch.Tensor, ax_in: O
 # trajectory back end: the reference's in-tree helpers interp_track, calc_min_bound_dists,
 # check_traj and the trajectory assembly of main_globaltraj.py:501-512, batched
 # ------------------------------------------------------------------------------------------------
+@_device_guard
 def interp_track_batch(pts: torch.Tensor, stepsize_approx: float = 1.0, n_pts: Optional[torch.Tensor] = None,
                        normvec: Optional[torch.Tensor] = None, normal_sign: float = 1.0, width_col: int = 2,
                        n_out_max: Optional[int] = None):
@@ -554,6 +608,7 @@ def interp_track_batch(pts: torch.Tensor, stepsize_approx: float = 1.0, n_pts: O
         n_out_max = need + 8
 
 
+@_device_guard
 def min_bound_dists_batch(xy: torch.Tensor, psi: torch.Tensor, bound1: torch.Tensor, bound2: torch.Tensor,
                           length_veh: float, width_veh: float, n_traj: Optional[torch.Tensor] = None,
                           nb1: Optional[torch.Tensor] = None, nb2: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -582,6 +637,7 @@ def min_bound_dists_batch(xy: torch.Tensor, psi: torch.Tensor, bound1: torch.Ten
 EXTREMA = ("min_dist", "kappa_abs_max", "ay_max", "ax_wo_drag_max", "ax_wo_drag_min", "a_tot_max", "vx_max", "n_points")
 
 
+@_device_guard
 def traj_extrema_batch(kappa: torch.Tensor, vx: torch.Tensor, ax: torch.Tensor, dragcoeff: float, mass_veh: float,
                        min_dists: Optional[torch.Tensor] = None, n_traj: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[B, 8] extrema per trajectory, columns as in EXTREMA (min_dist = inf without min_dists)."""
@@ -599,6 +655,7 @@ def traj_extrema_batch(kappa: torch.Tensor, vx: torch.Tensor, ax: torch.Tensor, 
     return ext
 
 
+@_device_guard
 def check_traj_batch(reftrack: torch.Tensor, normvec: torch.Tensor, xy: torch.Tensor, psi: torch.Tensor,
                      kappa: torch.Tensor, vx: torch.Tensor, ax: torch.Tensor, length_veh: float, width_veh: float,
                      dragcoeff: float, mass_veh: float, n_pts: Optional[torch.Tensor] = None,
@@ -637,6 +694,7 @@ def check_traj_flags(chk: dict, ggv, ax_max_machines, v_max: float, curvlim: flo
     return f
 
 
+@_device_guard
 def assemble_trajectory_batch(s: torch.Tensor, xy: torch.Tensor, psi: torch.Tensor, kappa: torch.Tensor, vx: torch.Tensor,
                               ax: torch.Tensor, spline_lengths: torch.Tensor, n_traj: Optional[torch.Tensor] = None,
                               n_spl: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -657,6 +715,7 @@ def assemble_trajectory_batch(s: torch.Tensor, xy: torch.Tensor, psi: torch.Tens
     return traj
 
 
+@_device_guard
 def check_normals_crossing_batch(track: torch.Tensor, normvec: torch.Tensor, horizon: int = 10,
                                  n_pts: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Batched tph.check_normals_crossing (/root/reference/helper_funcs_glob/src/prep_track.py:57-59): bool [B], True where

@@ -10,9 +10,12 @@
 namespace mc {
 size_t spline_ws_doubles(int n_max);
 size_t pdip_smem_bytes();
+int pdip_ctas_per_sm();
+int pdip_kappa_ctas_per_sm();
+int launch_debug_factor_solve(int, int, const int32_t *, double *, const Layout &, int32_t *, cudaStream_t);
 int debug_read_profile(unsigned long long *, int);
 void launch_mincurv_setup(int, int, const int32_t *, const double *, const double *, const double *, double,
-                          const double *, double *, const Layout &, int32_t *, cudaStream_t);
+                          const double *, double, double *, const Layout &, int32_t *, cudaStream_t);
 int launch_mincurv_pdip(int, int, const int32_t *, double *, const Layout &, const PdipParams &, double *, int32_t *,
                         int32_t *, int, int *, cudaStream_t);
 int launch_mincurv_pdip_kappa(int, int, const int32_t *, double *, const Layout &, const PdipParams &, double, double *,
@@ -35,7 +38,7 @@ int launch_shortest_path(int, int, const int32_t *, const double *, const double
                          int32_t *, int32_t *, double *, cudaStream_t);
 size_t vel_profile_ws_doubles(int n_max);
 int launch_vel_profile(int, int, int, const int32_t *, const double *, const double *, const double *, const double *,
-                       const double *, double, int, const double *, int, const double *, double, double, double, int,
+                       const double *, double, int, const double *, int, const double *, double, double, double, int, int,
                        double *, double *, double *, double *, int32_t *, double *, cudaStream_t);
 void launch_ax_t_profile(int, int, const int32_t *, const double *, int, const double *, const double *, double, double *,
                          double *, cudaStream_t);
@@ -70,6 +73,11 @@ static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 extern "C" {
 
 int mc_mincurv_kappa_batch(int, int, const int32_t *, double, double *, int32_t *, int32_t *, void *, size_t, void *);
+int mc_mincurv_solve_batch_ex(int, int, const int32_t *, const double *, const double *, const double *, double, double,
+                              const double *, double, double *, double *, double *, int32_t *, int32_t *, void *, size_t, void *);
+int mc_vel_profile_batch_ex(int, int, const int32_t *, const double *, const double *, const double *, int, const double *,
+                            const double *, double, int, const double *, int, const double *, double, double, double, int, int,
+                            double *, double *, double *, double *, int32_t *, void *, size_t, void *);
 
 int mc_version(void) { return 100; }
 const char *mc_last_error(void) { return g_err; }
@@ -112,15 +120,23 @@ static int mincurv_args(const char *who, int B, int n_max, void *workspace, size
     return MC_OK;
 }
 
+int mc_mincurv_setup_batch_ex(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
+                              const double *h, double w_veh, const double *w_veh_batch, double f_scale, int32_t *status,
+                              void *workspace, size_t workspace_bytes, void *stream) {
+    if (!reftrack || !normvec || !h || !status) return bad("mc_mincurv_setup_batch: NULL argument");
+    if (!(f_scale > 0.0)) return bad("mc_mincurv_setup_batch: f_scale must be positive");
+    int rc = mincurv_args("mc_mincurv_setup_batch", B, n_max, workspace, workspace_bytes);
+    if (rc) return rc;
+    mc::launch_mincurv_setup(B, n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, f_scale, (double *)workspace,
+                             mc::make_layout(n_max), status, (cudaStream_t)stream);
+    return check_cuda("mincurv_setup_kernel");
+}
+
 int mc_mincurv_setup_batch(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
                            const double *h, double w_veh, const double *w_veh_batch, int32_t *status, void *workspace,
                            size_t workspace_bytes, void *stream) {
-    if (!reftrack || !normvec || !h || !status) return bad("mc_mincurv_setup_batch: NULL argument");
-    int rc = mincurv_args("mc_mincurv_setup_batch", B, n_max, workspace, workspace_bytes);
-    if (rc) return rc;
-    mc::launch_mincurv_setup(B, n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, (double *)workspace,
-                             mc::make_layout(n_max), status, (cudaStream_t)stream);
-    return check_cuda("mincurv_setup_kernel");
+    return mc_mincurv_setup_batch_ex(B, n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, MC_F_SCALE_DEFAULT, status,
+                                     workspace, workspace_bytes, stream);
 }
 
 int mc_mincurv_pdip_batch(int B, int n_max, const int32_t *n_pts, double *alpha, int32_t *status, int32_t *iters,
@@ -139,7 +155,7 @@ int mc_mincurv_pdip_batch(int B, int n_max, const int32_t *n_pts, double *alpha,
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int per_sm = (int)((227 * 1024) / mc::pdip_smem_bytes());
+    int per_sm = mc::pdip_ctas_per_sm();
     if (const char *e = getenv("MC_DEBUG_PDIP_CTAS_PER_SM")) {      // occupancy experiments only (tools/prof_run.py)
         const int v = atoi(e);
         if (v > 0 && v < per_sm) per_sm = v;
@@ -170,10 +186,18 @@ int mc_mincurv_solve_batch(int B, int n_max, const int32_t *n_pts, const double 
                            const double *h, double kappa_bound, double w_veh, const double *w_veh_batch, double *alpha,
                            double *curv_error_max, double *kappa_lin_max, int32_t *status, int32_t *iters,
                            void *workspace, size_t workspace_bytes, void *stream) {
+    return mc_mincurv_solve_batch_ex(B, n_max, n_pts, reftrack, normvec, h, kappa_bound, w_veh, w_veh_batch, MC_F_SCALE_DEFAULT,
+                                     alpha, curv_error_max, kappa_lin_max, status, iters, workspace, workspace_bytes, stream);
+}
+
+int mc_mincurv_solve_batch_ex(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
+                              const double *h, double kappa_bound, double w_veh, const double *w_veh_batch, double f_scale,
+                              double *alpha, double *curv_error_max, double *kappa_lin_max, int32_t *status, int32_t *iters,
+                              void *workspace, size_t workspace_bytes, void *stream) {
     if (!reftrack || !normvec || !h || !alpha || !curv_error_max || !status)
         return bad("mc_mincurv_solve_batch: NULL argument");
-    int rc = mc_mincurv_setup_batch(B, n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, status, workspace,
-                                    workspace_bytes, stream);
+    int rc = mc_mincurv_setup_batch_ex(B, n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, f_scale, status, workspace,
+                                       workspace_bytes, stream);
     if (rc) return rc;
     rc = mc_mincurv_pdip_batch(B, n_max, n_pts, alpha, status, iters, workspace, workspace_bytes, stream);
     if (rc) return rc;
@@ -201,7 +225,7 @@ int mc_mincurv_kappa_batch(int B, int n_max, const int32_t *n_pts, double kappa_
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int per_sm = (int)((227 * 1024) / mc::pdip_smem_bytes());
+    const int per_sm = mc::pdip_kappa_ctas_per_sm();
     int grid = sms * (per_sm > 0 ? per_sm : 1);
     if (grid > B) grid = B;
     int *counter = (int *)((char *)workspace + mincurv_slabs_bytes(B, n_max));
@@ -341,6 +365,17 @@ int mc_vel_profile_batch(int B, int n_max, const int32_t *n_pts, const double *k
                          int n_ggv, const double *ggv, int n_mach, const double *ax_max_machines, double dyn_model_exp,
                          double drag_coeff, double m_veh, int filt_window, double *vx, double *ax, double *t,
                          double *laptime, int32_t *status, void *workspace, size_t workspace_bytes, void *stream) {
+    return mc_vel_profile_batch_ex(B, n_max, n_pts, kappa, el_lengths, mu, V, ggv_scale, v_max_batch, v_max, n_ggv, ggv, n_mach,
+                                   ax_max_machines, dyn_model_exp, drag_coeff, m_veh, filt_window, MC_VP_DECEL_SLICE_UPPER_DEFAULT,
+                                   vx, ax, t, laptime, status, workspace, workspace_bytes, stream);
+}
+
+int mc_vel_profile_batch_ex(int B, int n_max, const int32_t *n_pts, const double *kappa, const double *el_lengths,
+                            const double *mu, int V, const double *ggv_scale, const double *v_max_batch, double v_max,
+                            int n_ggv, const double *ggv, int n_mach, const double *ax_max_machines, double dyn_model_exp,
+                            double drag_coeff, double m_veh, int filt_window, int decel_slice_upper, double *vx, double *ax,
+                            double *t, double *laptime, int32_t *status, void *workspace, size_t workspace_bytes,
+                            void *stream) {
     if (B <= 0 || V <= 0 || n_max < 2 || !kappa || !el_lengths || !ggv || !ax_max_machines || !laptime || n_ggv < 1 ||
         n_mach < 1 || !(m_veh > 0.0) || !(dyn_model_exp > 0.0) || (!v_max_batch && !(v_max > 0.0)))
         return bad("mc_vel_profile_batch: bad argument");
@@ -352,8 +387,8 @@ int mc_vel_profile_batch(int B, int n_max, const int32_t *n_pts, const double *k
         return MC_EWORKSPACE;
     }
     if (mc::launch_vel_profile(B, V, n_max, n_pts, kappa, el_lengths, mu, ggv_scale, v_max_batch, v_max, n_ggv, ggv, n_mach,
-                               ax_max_machines, dyn_model_exp, drag_coeff, m_veh, filt_window, vx, ax, t, laptime, status,
-                               (double *)workspace, (cudaStream_t)stream) != 0)
+                               ax_max_machines, dyn_model_exp, drag_coeff, m_veh, filt_window, decel_slice_upper != 0, vx, ax, t,
+                               laptime, status, (double *)workspace, (cudaStream_t)stream) != 0)
         return bad("mc_vel_profile_batch: ggv / ax_max_machines tables are limited to 256 rows");
     return check_cuda("vel_profile_kernel");
 }
@@ -423,6 +458,18 @@ int mc_check_normals_crossing_batch(int B, int n_max, const int32_t *n_pts, cons
         return bad("mc_check_normals_crossing_batch: bad argument");
     mc::launch_normals_crossing(B, n_max, n_pts, track, normvec, horizon, crossing, (cudaStream_t)stream);
     return check_cuda("normals_crossing_kernel");
+}
+
+/* debug aid (tests/test_gpu_factor.py): one factorisation + the two kinds of solve of the interior-point kernel on slabs
+ * whose H band, V_DD, V_RHS and V_T0 the caller has filled in; results in V_DX, V_T1, V_T2 */
+int mc_debug_factor_solve(int B, int n_max, const int32_t *n_pts, int32_t *status, void *workspace, size_t workspace_bytes,
+                          void *stream) {
+    if (!status) return bad("mc_debug_factor_solve: NULL argument");
+    int rc = mincurv_args("mc_debug_factor_solve", B, n_max, workspace, workspace_bytes);
+    if (rc) return rc;
+    if (mc::launch_debug_factor_solve(B, n_max, n_pts, (double *)workspace, mc::make_layout(n_max), status, (cudaStream_t)stream) != 0)
+        return bad("mc_debug_factor_solve: cudaFuncSetAttribute failed");
+    return check_cuda("debug_factor_solve_kernel");
 }
 
 int mc_debug_read_profile(unsigned long long *host_out16, int reset) {

@@ -21,7 +21,7 @@ constexpr int ZB_PITCH = 108;    // per-point scratch row of the assembly: three
 constexpr int HBW = 32;          // half-bandwidth kept of H = E^T E (truncation error ~1e-10 on alpha)
 constexpr int HB_PITCH = 34;     // 33 used, padded so that a row is a multiple of 16 bytes
 constexpr int N_MIN = 80;        // smallest supported closed track (band must not wrap onto itself)
-constexpr double F_SCALE = 2.0;  // tph: f carries a factor 2 that H does not
+constexpr double F_SCALE_DEFAULT = 2.0;  // tph: f carries a factor 2 that H does not; run-time parameter f_scale of mc_mincurv_setup_batch_ex
 constexpr double FIX_EPS = 1e-8; // half-width given to variables whose box has collapsed (lb == ub)
 
 __device__ __forceinline__ int wrapi(int i, int n) {

@@ -24,7 +24,7 @@ namespace mc {
 __global__ void __launch_bounds__(256)
 mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
                      const double *__restrict__ reftrack, const double *__restrict__ normvec,
-                     const double *__restrict__ hin, double w_veh, const double *__restrict__ w_veh_batch,
+                     const double *__restrict__ hin, double w_veh, const double *__restrict__ w_veh_batch, double f_scale,
                      double *__restrict__ ws, Layout L, int32_t *__restrict__ status) {
     const int b = blockIdx.x;
     const int n = n_pts ? n_pts[b] : n_max;
@@ -114,7 +114,7 @@ mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
         const double hi = H[i], him = H[im1];
         const double zx = 6.0 * ((T4[ip1] - T4[i]) / hi - (T4[i] - T4[im1]) / him);
         const double zy = 6.0 * ((T5[ip1] - T5[i]) / hi - (T5[i] - T5[im1]) / him);
-        F[i] = F_SCALE * (NY[i] * zy - NX[i] * zx);
+        F[i] = f_scale * (NY[i] * zy - NX[i] * zx);
     }
     __syncthreads();
     assemble_hband(slab, L, n, nullptr, s_win);
@@ -124,15 +124,12 @@ mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
 }
 
 void launch_mincurv_setup(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
-                          const double *h, double w_veh, const double *w_veh_batch, double *ws, const Layout &L,
-                          int32_t *status, cudaStream_t stream) {
+                          const double *h, double w_veh, const double *w_veh_batch, double f_scale, double *ws,
+                          const Layout &L, int32_t *status, cudaStream_t stream) {
     constexpr int smem = hband_win_doubles(256) * (int)sizeof(double);      // 49 KB: above the static limit
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(mincurv_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        configured = true;
-    }
-    mincurv_setup_kernel<<<B, 256, smem, stream>>>(n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, ws, L, status);
+    // (per launch: the attribute is per device and a process may drive several)
+    cudaFuncSetAttribute(mincurv_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    mincurv_setup_kernel<<<B, 256, smem, stream>>>(n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, f_scale, ws, L, status);
 }
 
 }  // namespace mc

@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(128, 5) vel_profile_kernel(const VpArgs a) {
     const int n = a.n_pts ? a.n_pts[b] : a.n_max;
     if (n < 2 || n > a.n_max) {          // inactive / invalid track: no profile
         a.laptime[p] = 0.0;
-        if (a.status) a.status[p] = (n <= 0) ? vp::VP_STATUS_OK : MC_STATUS_BREAKDOWN;
+        // n == 0: an inactive slot (ok); n < 0: the producer reported an overflow (create_raceline's -needed) -- never a lap time
+        if (a.status) a.status[p] = (n == 0) ? vp::VP_STATUS_OK : MC_STATUS_BREAKDOWN;
         return;
     }
     vp::Tables tb{gv, gax, gay, a.n_ggv, mv, ma, a.n_mach};
@@ -76,14 +77,15 @@ __global__ void __launch_bounds__(128, 5) vel_profile_kernel(const VpArgs a) {
 int launch_vel_profile(int B, int V, int n_max, const int32_t *n_pts, const double *kappa, const double *el,
                        const double *mu, const double *ggv_scale, const double *v_max_batch, double v_max, int n_ggv,
                        const double *ggv, int n_mach, const double *mach, double dyn_model_exp, double drag_coeff,
-                       double m_veh, int filt_window, double *vx, double *ax, double *t, double *laptime, int32_t *status,
-                       double *ws, cudaStream_t stream) {
+                       double m_veh, int filt_window, int decel_slice_upper, double *vx, double *ax, double *t, double *laptime,
+                       int32_t *status, double *ws, cudaStream_t stream) {
     if (n_ggv > VP_TAB_MAX || n_mach > VP_TAB_MAX) return -1;
     VpArgs a;
     a.B = B; a.V = V; a.n_max = n_max; a.n_pts = n_pts; a.kappa = kappa; a.el = el; a.mu = mu;
     a.ggv_scale = ggv_scale; a.v_max_batch = v_max_batch; a.v_max = v_max; a.n_ggv = n_ggv; a.n_mach = n_mach;
     a.ggv = ggv; a.mach = mach;
     a.pr.dyn_model_exp = dyn_model_exp; a.pr.drag_coeff = drag_coeff; a.pr.m_veh = m_veh; a.pr.filt_window = filt_window;
+    a.pr.decel_slice_upper = decel_slice_upper;
     a.vx = vx; a.ax = ax; a.t = t; a.laptime = laptime; a.status = status; a.ws = ws;
     const size_t P = (size_t)B * V;
     const int threads = 128;

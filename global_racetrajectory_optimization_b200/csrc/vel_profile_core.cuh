@@ -27,12 +27,12 @@ namespace vp {
 
 // tph (as recalled) keeps vx_profile_double[no_points:] after the backward pass over the doubled lap, i.e. the half the
 // backward pass visits first.  Cannot be confirmed offline (parity unpinned); oracle/tph_velprofile.py carries the same
-// switch (DECEL_LAP_SLICE_UPPER).  false => the backward pass runs both laps and keeps the second one.
-// tests/host_harness builds both settings (-DVP_DECEL_SLICE_UPPER=0/1) against the oracle's.
+// switch (DECEL_LAP_SLICE_UPPER).  It is a RUN-TIME parameter (Params::decel_slice_upper, C-ABI mc_vel_profile_batch_ex):
+// 0 => the backward pass runs both laps and keeps the second one.  VP_DECEL_SLICE_UPPER is only the default
+// (tools/pin_against_tph.py reports which value the real package implies).
 #ifndef VP_DECEL_SLICE_UPPER
 #define VP_DECEL_SLICE_UPPER 1
 #endif
-constexpr bool VP_DECEL_LAP_SLICE_UPPER = (VP_DECEL_SLICE_UPPER != 0);
 
 constexpr int VP_UNROLL = 4;             // elements per block of the streaming loops (loads first, then arithmetic)
 constexpr int VP_STATUS_OK = 0;
@@ -70,6 +70,7 @@ struct Tables {
 struct Params {
     double dyn_model_exp, drag_coeff, m_veh;
     int filt_window;                // <= 1: no moving-average filter (tph: filt_window=None)
+    int decel_slice_upper = VP_DECEL_SLICE_UPPER;   // which half of the doubled lap the backward pass keeps (see above)
 };
 
 struct Strided {
@@ -270,7 +271,8 @@ VP_HD int profile_thread(int n, const double *kappa, const double *el, const dou
     // the step from original point m to m-1 uses el[m], as in tph).  Point i1 of step j is point i0 of step j + 1, so
     // each step loads one new point, one step ahead.
     {
-        const int j_end = VP_DECEL_LAP_SLICE_UPPER ? n - 1 : 2 * n - 1;
+        const bool slice_upper = pr.decel_slice_upper != 0;
+        const int j_end = slice_upper ? n - 1 : 2 * n - 1;
         bool active = false;
         double cur = V[n - 1], prev0 = cur, dprev = 0.0;
         double r0 = R[n - 1], e0 = EL[n - 1], m0 = has_mu ? (double)MU[n - 1] : 1.0;
@@ -299,7 +301,7 @@ VP_HD int profile_thread(int n, const double *kappa, const double *el, const dou
                 if (vpn < nxt0) nxt = vpn;
                 if (vpn > v_max) active = false;
             }
-            if (VP_DECEL_LAP_SLICE_UPPER || j + 1 >= n) V[i1] = nxt;
+            if (slice_upper || j + 1 >= n) V[i1] = nxt;
             cur = nxt;
             prev0 = nxt0;
             dprev = dj;

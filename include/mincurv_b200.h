@@ -41,6 +41,15 @@ extern "C" {
 #define MC_STATUS_BREAKDOWN 3
 #define MC_STATUS_KAPPA_ACTIVE 4
 
+/* The two constants of the third-party package that cannot be confirmed offline (parity unpinned).
+ * They are RUN-TIME parameters of the *_ex entry points; the plain entry points use these defaults.
+ * tools/pin_against_tph.py determines both from the real trajectory_planning_helpers when it is importable.
+ *   f_scale            tph.opt_min_curv: f = f_scale * E^T k_ref (tph as recalled: the linear term carries a factor 2 the
+ *                      quadratic term does not; 1.0 would be the consistent Gauss-Newton scaling)
+ *   decel_slice_upper  tph.calc_vel_profile (closed): which half of the doubled lap is kept after the backward pass */
+#define MC_F_SCALE_DEFAULT 2.0
+#define MC_VP_DECEL_SLICE_UPPER_DEFAULT 1
+
 /* library version (major*10000 + minor*100 + patch) and last CUDA error text of this thread */
 int mc_version(void);
 const char *mc_last_error(void);
@@ -87,6 +96,14 @@ int mc_mincurv_solve_batch(int B, int n_max, const int32_t *n_pts,
                            int32_t *status, int32_t *iters,
                            void *workspace, size_t workspace_bytes, void *stream);
 
+/* the same with an explicit f_scale (see MC_F_SCALE_DEFAULT) */
+int mc_mincurv_solve_batch_ex(int B, int n_max, const int32_t *n_pts,
+                              const double *reftrack, const double *normvec, const double *h,
+                              double kappa_bound, double w_veh, const double *w_veh_batch, double f_scale,
+                              double *alpha, double *curv_error_max, double *kappa_lin_max,
+                              int32_t *status, int32_t *iters,
+                              void *workspace, size_t workspace_bytes, void *stream);
+
 /* The three stages of mc_mincurv_solve_batch as separate stream-ordered calls on the same workspace
  * (assembly of the banded QP, interior-point solve, post-solve curvature check / linearisation error);
  * mc_mincurv_solve_batch is exactly setup -> pdip -> finalize.  Exposed so that a caller can time or
@@ -94,6 +111,9 @@ int mc_mincurv_solve_batch(int B, int n_max, const int32_t *n_pts,
 int mc_mincurv_setup_batch(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
                            const double *h, double w_veh, const double *w_veh_batch, int32_t *status,
                            void *workspace, size_t workspace_bytes, void *stream);
+int mc_mincurv_setup_batch_ex(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
+                              const double *h, double w_veh, const double *w_veh_batch, double f_scale, int32_t *status,
+                              void *workspace, size_t workspace_bytes, void *stream);
 int mc_mincurv_pdip_batch(int B, int n_max, const int32_t *n_pts, double *alpha, int32_t *status, int32_t *iters,
                           void *workspace, size_t workspace_bytes, void *stream);
 int mc_mincurv_finalize_batch(int B, int n_max, const int32_t *n_pts, const double *alpha, double kappa_bound,
@@ -187,6 +207,13 @@ int mc_vel_profile_batch(int B, int n_max, const int32_t *n_pts, const double *k
                          double dyn_model_exp, double drag_coeff, double m_veh, int filt_window,
                          double *vx, double *ax, double *t, double *laptime, int32_t *status,
                          void *workspace, size_t workspace_bytes, void *stream);
+/* the same with an explicit decel_slice_upper (see MC_VP_DECEL_SLICE_UPPER_DEFAULT) */
+int mc_vel_profile_batch_ex(int B, int n_max, const int32_t *n_pts, const double *kappa, const double *el_lengths,
+                            const double *mu, int V, const double *ggv_scale, const double *v_max_batch, double v_max,
+                            int n_ggv, const double *ggv, int n_mach, const double *ax_max_machines,
+                            double dyn_model_exp, double drag_coeff, double m_veh, int filt_window, int decel_slice_upper,
+                            double *vx, double *ax, double *t, double *laptime, int32_t *status,
+                            void *workspace, size_t workspace_bytes, void *stream);
 
 /* tph.calc_ax_profile.calc_ax_profile(vx_profile, el_lengths, eq_length_output=False) and
  * tph.calc_t_profile.calc_t_profile(vx_profile, el_lengths, t_start, ax_profile) stand-alone
@@ -258,6 +285,14 @@ int mc_check_normals_crossing_batch(int B, int n_max, const int32_t *n_pts, cons
 /* Debug aid (synchronous): reads (and optionally clears) 24 cycle counters that CTA 0 of mincurv_pdip_kernel
  * accumulates per phase -- used by tools/prof_run.py to attribute time inside the kernel. Host pointer. */
 int mc_debug_read_profile(unsigned long long *host_out24, int reset);
+
+/* Debug aid (tests/test_gpu_factor.py): runs the linear algebra of one interior-point iteration of
+ * mincurv_pdip_kernel -- the bordered LDL^T factorisation of M = H + D and both kinds of solve -- on slabs whose
+ * H band, D (slab vector DD), and right-hand sides (slab vectors RHS, T0) the caller has filled in; the solutions
+ * M^-1 RHS, M^-1 T0 (full sweeps), M^-1 T0 (forward sweep fused into a second factorisation) are left in the slab
+ * vectors DX, T1, T2.  status[b] = 3 on a non-positive pivot.  Workspace as for mc_mincurv_solve_batch. */
+int mc_debug_factor_solve(int B, int n_max, const int32_t *n_pts, int32_t *status, void *workspace, size_t workspace_bytes,
+                          void *stream);
 
 #ifdef __cplusplus
 }

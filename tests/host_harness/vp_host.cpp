@@ -14,7 +14,7 @@ extern "C" int vp_host_profile(int n, const double *kappa, const double *el, con
     for (int k = 0; k < n_ggv; ++k) { gv[k] = ggv[3 * k]; gax[k] = ggv[3 * k + 1]; gay[k] = ggv[3 * k + 2]; }
     for (int k = 0; k < n_mach; ++k) { mv[k] = mach[2 * k]; ma[k] = mach[2 * k + 1]; }
     Tables tb{gv.data(), gax.data(), gay.data(), n_ggv, mv.data(), ma.data(), n_mach};
-    Params pr{dyn_model_exp, drag_coeff, m_veh, filt_window};
+    Params pr{dyn_model_exp, drag_coeff, m_veh, filt_window, VP_DECEL_SLICE_UPPER};
     // same addressing as the kernel: vector k of the profile at ws + k * n * stride + p, element stride `stride`
     const size_t P = (size_t)stride, p = (size_t)(stride - 1), vec = (size_t)n * P;
     std::vector<double> ws(5 * vec, -777.0);

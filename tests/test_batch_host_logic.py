@@ -37,6 +37,9 @@ def fake(monkeypatch):
     monkeypatch.setattr(B_, "_stream", lambda: None)
     monkeypatch.setattr(B_, "_chunk", lambda B, per_item, dev: max(1, B // 2))      # force the chunked paths
     monkeypatch.setattr(B_, "_WS", {})
+    # the stand-in writes nothing: what the wrappers allocate with torch.empty would be uninitialised memory (a NaN in
+    # alpha used to reach create_raceline_batch's capacity estimate from time to time)
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: torch.zeros(*a, **k))
     return lib
 
 
@@ -50,7 +53,7 @@ def test_every_wrapper_matches_the_signature_table(fake):
     npts = torch.full((B,), n, dtype=torch.int32)
     cx, cy, nv, h = B_.calc_splines_batch(rt, n_pts=npts)
     res = B_.opt_min_curv_batch(rt, nv, h, 0.12, torch.full((B,), 2.0, dtype=torch.float64), n_pts=npts)
-    assert _names(fake).count("mc_mincurv_solve_batch") == 3                        # 5 tracks in chunks of 2
+    assert _names(fake).count("mc_mincurv_solve_batch_ex") == 3                     # 5 tracks in chunks of 2
     assert res["alpha"].shape == (B, n)
     alpha = torch.zeros((B, n), dtype=torch.float64)      # (the stand-in library writes nothing: outputs are uninitialised)
     B_.opt_shortest_path_batch(rt, nv, 2.0, n_pts=npts)
@@ -62,10 +65,10 @@ def test_every_wrapper_matches_the_signature_table(fake):
     mach = np.array([[0.0, 5.0], [80.0, 5.0]])
     kap, el = torch.rand((B, 200), dtype=torch.float64), torch.ones((B, 200), dtype=torch.float64)
     vp = B_.vel_profile_batch(kap, el, ggv, mach, 70.0, 0.75, 1200.0, n_pts=torch.full((B,), 200, dtype=torch.int32))
-    assert vp["vx"].shape == (B, 1, 200) and vp["t"].shape == (B, 1, 201) and _names(fake).count("mc_vel_profile_batch") == 3
+    assert vp["vx"].shape == (B, 1, 200) and vp["t"].shape == (B, 1, 201) and _names(fake).count("mc_vel_profile_batch_ex") == 3
     ltm = B_.lap_time_matrix_batch(kap, el, ggv, mach, [0.5, 1.0], [30.0, 40.0, 50.0], 0.75, 1200.0)
     assert ltm.shape == (B, 3, 2)
-    last = [c for c in fake.calls if c[0] == "mc_vel_profile_batch"][-1][1]
+    last = [c for c in fake.calls if c[0] == "mc_vel_profile_batch_ex"][-1][1]
     assert last[6] == 6                                                              # V = 3 top speeds x 2 ggv scales
     B_.calc_ax_t_profile_batch(torch.rand((B, 201), dtype=torch.float64), el)
     out, n_out = B_.interp_track_batch(rt, 1.0, n_pts=npts)
@@ -81,8 +84,10 @@ def test_every_wrapper_matches_the_signature_table(fake):
     with pytest.raises(RuntimeError, match="too large"):
         B_.check_normals_crossing_batch(rt, nv, n, n_pts=npts)
     used = set(_names(fake))
-    assert used >= set(_lib.EXPORTED_SYMBOLS) - {"mc_version", "mc_last_error", "mc_debug_read_profile", "mc_mincurv_setup_batch",
-                                                 "mc_mincurv_pdip_batch", "mc_mincurv_finalize_batch", "mc_mincurv_kappa_batch"}
+    assert used >= set(_lib.EXPORTED_SYMBOLS) - {"mc_version", "mc_last_error", "mc_debug_read_profile", "mc_debug_factor_solve",
+                                                 "mc_mincurv_setup_batch", "mc_mincurv_setup_batch_ex", "mc_mincurv_solve_batch",
+                                                 "mc_vel_profile_batch", "mc_mincurv_pdip_batch", "mc_mincurv_finalize_batch",
+                                                 "mc_mincurv_kappa_batch"}
 
 
 def test_launches_with_the_track_index_on_grid_y_are_chunked(fake, monkeypatch):
@@ -106,8 +111,8 @@ def test_globaltraj_batch_wires_the_stages_in_the_reference_order(fake, opt_type
     mach = np.array([[0.0, 5.0], [80.0, 5.0]])
     out = globaltraj.globaltraj_batch(rt, opt_type, globaltraj.default_pars(), ggv, mach)
     order = [nm for nm in _names(fake) if not nm.endswith("_workspace_bytes")]
-    qp = "mc_mincurv_solve_batch" if opt_type == "mincurv" else "mc_shortest_path_solve_batch"
-    want = ["mc_calc_splines_batch", qp, "mc_create_raceline_batch", "mc_vel_profile_batch", "mc_assemble_trajectory_batch",
+    qp = "mc_mincurv_solve_batch_ex" if opt_type == "mincurv" else "mc_shortest_path_solve_batch"
+    want = ["mc_calc_splines_batch", qp, "mc_create_raceline_batch", "mc_vel_profile_batch_ex", "mc_assemble_trajectory_batch",
             "mc_interp_track_batch", "mc_min_bound_dists_batch", "mc_traj_extrema_batch"]
     stages = [nm for k, nm in enumerate(order) if nm in want and (k == 0 or order[k - 1] != nm)]    # chunked launches collapse
     assert stages == want
@@ -126,13 +131,13 @@ def test_iqp_batch_grows_its_buffers_when_a_resampled_track_does_not_fit(fake, m
 
     def patched(self, name):
         fn = real_getattr(self, name)
-        if name == "mc_mincurv_solve_batch":
+        if name == "mc_mincurv_solve_batch_ex":
             def solve(*a):
                 fn(*a)
                 bq, nmax = a[0], a[1]
-                ctypes.memset(a[9].value, 0, bq * nmax * 8)                      # alpha = 0
-                ctypes.memset(a[10].value, 0, bq * 8)                            # curv_error_max = 0 (converged once iter >= iters_min)
-                ctypes.memset(a[12].value, 0, bq * 4)                            # status = 0
+                ctypes.memset(a[10].value, 0, bq * nmax * 8)                     # alpha = 0
+                ctypes.memset(a[11].value, 0, bq * 8)                            # curv_error_max = 0 (converged once iter >= iters_min)
+                ctypes.memset(a[13].value, 0, bq * 4)                            # status = 0
                 return 0
             return solve
         if name != "mc_iqp_relinearise_batch":
