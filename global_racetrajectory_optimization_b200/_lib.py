@@ -73,8 +73,8 @@ def load(build_if_missing: bool = True):
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB_PATH
-    if build_if_missing and _build.needs_build():
+    path = os.environ.get("MC_B200_LIB") or _build.LIB_PATH      # (override: the instrumented build of tools/prof_run.py)
+    if path == _build.LIB_PATH and build_if_missing and _build.needs_build():
         _build.build()
     if not os.path.exists(path):
         raise MinCurvLibError(f"{path} is missing: build it with `python -m global_racetrajectory_optimization_b200.build` "

@@ -41,7 +41,7 @@ _WS = {}
 # mirror of csrc/mincurv_ws.cuh (debugging / tests read intermediate results out of the workspace)
 SLAB_VECTORS = ("H DIAG DFW DBW LFW INVD TII RHOP RHOM PX PY NX NY MX MY XP YP SX SY KREF LB UB F "
                 "T0 T1 T2 T3 T4 T5 ALPHA LU LL RD RHS DX DD DLU DLL SU SL ISU ISL YPAD "
-                "S3 S4 L3 L4 KL WK EDX T3K T4K VV IH WP TP").split()
+                "S3 S4 L3 L4 KL WK EDX T3K T4K VV IH").split()
 HB_PITCH = 34
 ZB_PITCH = 108
 
@@ -55,7 +55,7 @@ def mincurv_slab_layout(n_max: int) -> dict:
     o_hb = o
     o += np_ * HB_PITCH
     o_tiles = o
-    o += np_ * (32 + 33)
+    o += np_ * 68
     return dict(np=np_, nb_max=nb_max, o_zb=o_zb, o_hb=o_hb, o_tiles=o_tiles, stride=(o + 15) & ~15)
 
 

@@ -31,6 +31,20 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+PROFILE_LIB_PATH = os.path.join(_HERE, "libmincurv_b200_prof.so")
+
+
+def build_profile(verbose: bool = False, extra=(), out=None) -> str:
+    """Instrumented build (-DMC_PROFILE: cycle counters inside the interior-point kernel, read with mc_debug_read_profile);
+    a separate file, loaded only when MC_B200_LIB points at it (tools/prof_run.py).  Never the product library."""
+    out = out or PROFILE_LIB_PATH
+    cmd = [_nvcc(), *NVCC_FLAGS, "-DMC_PROFILE", *extra, "-o", out, *[os.path.join(CSRC, s) for s in SOURCES]]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH

@@ -21,10 +21,12 @@
 // (profiles/r01_final_pdip_ncu_summary.json).  Here every step offers 64 independent DFMAs per instance and eight
 // instances share an SM, so the fp64 pipe and the issue slots are what is busy.
 //
-// The factor (L: 32 doubles per column, G: 32 + 1 pad, plus the vectors 1/d and y) goes to the instance's HBM slab and
+// The factor (34 doubles per column of L and of G: 32 entries + the sweeps' per-column scalars) goes to the instance's HBM slab and
 // is streamed back by the triangular sweeps through a shared-memory ring of 8-column units filled by cp.async.bulk
 // (TMA, 1-D) on mbarriers -- the band rows of H reach warp 0 the same way.  Per iteration: factor written once, read
 // three times (the predictor's forward sweep is fused into the factorisation).
+#include <cstdio>
+#include <cstdlib>
 #include "mincurv_ops.cuh"
 
 namespace mc {
@@ -32,16 +34,14 @@ namespace mc {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int IP_THREADS = 64;
 constexpr int SUB = 8;                 // columns per hand-off / streaming unit
-constexpr int LTS = 34;                // shared pitch of a factor column staged for the fill warp: [l(32), w, y]
-constexpr int GTS = 33;                // pitch of a fill column [g(32), pad] (HBM and shared: odd => conflict-free row-owner reads)
-constexpr int LTG = 32;                // HBM pitch of a factor column
-constexpr int HB_SLOTS = 3;            // band-row units in flight for warp 0
-constexpr int LT_SLOTS = 3;            // factor-column units between warp 0 and warp 1
+constexpr int VBP = 12;                // pitch of the row-major panel buffers (conflict-free DMMA fragment loads, 16-byte rows)
+constexpr int FROW = 34;               // HBM (and sweep-ring) pitch of a factor row: [l or g (32), t or z, w]
+constexpr int HB_SLOTS = 2;            // band-row units of warp 0 (the next panel's is in flight)
+constexpr int HO_SLOTS = 2;            // panels between warp 0 and warp 1
 constexpr int RING_UNITS = 7;          // sweep ring: 32-row window (5 units) + 2 units of prefetch
-constexpr int RING_UNIT_DOUBLES = SUB * GTS;          // 264 (a unit of L is 256)
+constexpr int RING_UNIT_DOUBLES = SUB * FROW;         // 272
 constexpr unsigned HB_UNIT_BYTES = SUB * HB_PITCH * sizeof(double);   // 2176
-constexpr unsigned LT_UNIT_BYTES = SUB * LTG * sizeof(double);        // 2048
-constexpr unsigned GT_UNIT_BYTES = SUB * GTS * sizeof(double);        // 2112
+constexpr unsigned FUNIT_BYTES = SUB * FROW * sizeof(double);         // 2176
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -59,10 +59,34 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// try_wait suspends the thread for a hardware-defined time before it reports failure: the loop is not a busy spin
+#ifndef MC_WAIT_MODE
+#define MC_WAIT_MODE 1
+#endif
+// MC_WAIT_MODE 0: try_wait with a long suspend hint (the thread is parked until the phase completes);
+//              1: test_wait spin (non-blocking probe): the waiter resumes within a few cycles of the arrival.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+#if MC_WAIT_MODE == 0
     asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"
                  " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+#else
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
+}
+// same, for the warp that is normally AHEAD of its producer (the fill warp): back off between probes so that the
+// probes do not take issue slots from the chain warps of the same scheduler
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, unsigned parity) {
+#if MC_WAIT_MODE == 0
+    mbar_wait(bar, parity);
+#else
+    unsigned ok = 0;
+    for (;;) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(20);
+    }
+#endif
 }
 // The factor is a stream (written once, read three times per iteration, 0.5 MB per instance, far beyond what L2 can
 // keep for 1184 resident instances): its copies and stores carry an evict-first L2 policy so that they do not push the
@@ -83,9 +107,21 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 __device__ unsigned long long g_prof[24];
 #define PROF_T0(name) const long long name = clock64()
 #define PROF_ADD(slot, t0) do { if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_prof[slot], (unsigned long long)(clock64() - (t0))); } while (0)
+#define PROF_ADD1(slot, t0) do { if (blockIdx.x == 0 && threadIdx.x == 32) atomicAdd(&g_prof[slot], (unsigned long long)(clock64() - (t0))); } while (0)
+__device__ unsigned long long g_seg[32];
+#ifdef MC_PROFILE_SEG      // per-panel sub-phase marks: ~200 cycles each, only for attributing time inside one panel
+#define SEG_BEGIN() long long _seg_t = clock64()
+#define SEG(slot) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) { const long long _n = clock64(); atomicAdd(&g_seg[slot], (unsigned long long)(_n - _seg_t)); _seg_t = _n; } } while (0)
 #else
+#define SEG_BEGIN() do { } while (0)
+#define SEG(slot) do { } while (0)
+#endif
+#else
+#define SEG_BEGIN() do { } while (0)
+#define SEG(slot) do { } while (0)
 #define PROF_T0(name) do { } while (0)
 #define PROF_ADD(slot, t0) do { } while (0)
+#define PROF_ADD1(slot, t0) do { } while (0)
 #endif
 
 // 1/d for a positive, normal d: hardware seed (rcp.approx.f64, ~20 bits) + two Newton steps (relative error ~1e-16).
@@ -105,12 +141,19 @@ __device__ __forceinline__ double mask_hi(double x, int m) {
     return __hiloint2double(__double2hiint(x) & m, __double2loint(x));
 }
 
+// one panel (eight columns) handed from warp 0 to warp 1
+struct Handoff {
+    double vb[32 * VBP];       // L of the window rows k0+8 .. k0+39 x the panel's 8 columns, row-major (DMMA fragments)
+    double l11[64];            // the panel's unit-lower diagonal block, row-major [m][j] (m > j used)
+    double w[8], y[8];         // 1/d and the forward-substituted right-hand side of the panel's columns
+};
+
 struct IpShared {
     union {
         struct {
             double hb[HB_SLOTS][SUB * HB_PITCH];      // band rows of H staged for warp 0 (TMA)
-            double lt[LT_SLOTS][SUB * LTS];           // factor columns, warp 0 -> warp 1
-            double gt[SUB * GTS];                     // fill columns of the current unit (warp 1: S update)
+            Handoff ho[HO_SLOTS];                     // warp 0 -> warp 1
+            double gb[32 * VBP];                      // warp 1: the panel of the fill rows, row-major (DMMA fragments)
         } f;
         double ring[RING_UNITS][RING_UNIT_DOUBLES];   // sweeps: streamed factor units
         double win[hband_win_doubles(IP_THREADS)];    // K2b': scratch of the weighted band assembly
@@ -119,22 +162,24 @@ struct IpShared {
         double Ss[32 * 33];                           // separator block -> its L_S (strictly lower, in place)
         double sfrag[20 * 32];                        // during the chain: S accumulators (DMMA C fragments, lane-major)
     } s;
-    double cb[2][36];                                 // warp 0: column broadcast [v(32), pivot, y, -, -], double buffered
-    double wS[32], xs[32], gs[32], part[2][32];
+    double wS[32], gs[32], part[2][32];
     double red[32];
-    uint64_t hb_full[HB_SLOTS], lt_full[LT_SLOTS], lt_empty[LT_SLOTS], ring_full[RING_UNITS];
+    uint64_t hb_full[HB_SLOTS], ho_full[HO_SLOTS], ho_empty[HO_SLOTS], ring_full[RING_UNITS];
     unsigned ring_phase;                              // parity bit per ring slot
     int flag;
     int next;                                         // next instance index (dynamic work distribution)
 };
 
-// pointers into the instance slab that the factorisation and the sweeps use
+// pointers into the instance slab that the factorisation and the sweeps use.  Factor rows in HBM (pitch 34 doubles, so
+// that a unit of eight rows is one 2176-byte bulk copy and every row is 16-byte aligned):
+//   LT[k] = [ L[k+1 .. k+32][k],  t_k,  w_k ]      t = (y - G^T x_S) w: right-hand side of the backward sweep, w = 1/d_k
+//   GT[k] = [ G[0 .. 31][k],      z_k,  w_k ]      z = w y: what the separator's forward substitution needs
+// so the sweeps read nothing but the streamed units (no per-column global loads on the serial chains).  Columns
+// NA .. 8 ceil(NA / 8) - 1 are padding (pivot 1, nothing else): every unit is a full panel.
 struct Factor {
     const double *HB;      // band of H, row i: H[i][i .. i+32], [33]: pivot H_ii + D_i (written by factor())
     const double *DD;      // barrier diagonal
-    double *LT;            // [NA][32]  unit-lower factor columns: LT[k][rho] = L[k+1+rho][k]
-    double *GT;            // [NA][33]  fill columns: GT[k][r] = G[r][k]
-    double *WP, *YP, *TP;  // [NA] 1/d_k, forward-substituted rhs, backward rhs (y - G^T x_S) / d
+    double *LT, *GT;
     int n, NA;
 };
 
@@ -143,164 +188,263 @@ __device__ __forceinline__ Factor make_factor(double *slab, const Layout &L, int
     F.HB = slab + L.o_hb;
     F.DD = vec(slab, L, V_DD);
     F.LT = slab + L.o_tiles;
-    F.GT = F.LT + (size_t)L.np * LTG;
-    F.WP = vec(slab, L, V_WP);
-    F.YP = vec(slab, L, V_YPAD);
-    F.TP = vec(slab, L, V_TP);
+    F.GT = F.LT + (size_t)L.np * FROW;
     F.n = n;
     F.NA = n - 32;
     return F;
 }
 
-// ---- warp 0: LDL^T of the chain, column by column, with the forward substitution of g fused in ----
-__device__ __noinline__ bool factor_chain(IpShared &sh, const Factor F, const double *__restrict__ g, unsigned tick) {
+__device__ __forceinline__ int blk(int I, int J) { return (I * (I + 1)) / 2 + J; }      // lower 8x8 block (I >= J) of a 4x4 block grid
+
+// ---- warp 0: LDL^T of the chain, one panel of eight columns at a time, with the forward substitution of g fused in.
+//      The 32x32 window of accumulated updates (rows/columns k0 .. k0+31, lower blocks) lives in DMMA C fragments.
+//      Panel step: (1) block column 0 -> row layout (lane l = row k0 + l; lanes 0..7 also carry the entering row
+//      k0 + 32 + l); (2) eight pivots: d_j by shuffle from lane j, w = 1/d, l = v w, v_{j',j} by shuffle from lane j'
+//      for the in-panel updates; (3) trailing update W'[I][J] = W[I+1][J+1] + (L d)(L)^T on the tensor cores, which also
+//      slides the window by one block (the block row of the eight entering rows starts from zero). ----
+__device__ __noinline__ bool factor_chain(IpShared &sh, const double *__restrict__ HBp, double *__restrict__ LTp, double *__restrict__ GTp, const int NA, const double *__restrict__ g, unsigned tick) {
     const int lane = threadIdx.x & 31;
-    const int NA = F.NA;
+    const int gq = lane >> 2, q = lane & 3;
     const int nunits = (NA + SUB - 1) / SUB;
     const uint64_t pol = l2_evict_first_policy();
-    double acc[32];
+    double W[10][2];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) acc[c] = 0.0;
-    double gacc = 0.0;
-    double gk = (lane < NA) ? g[lane] : 0.0;          // rhs entry of the row this lane finishes next
+    for (int b = 0; b < 10; ++b) { W[b][0] = 0.0; W[b][1] = 0.0; }
+    // right-hand side: gv = g - (L y so far) of row k0 + lane; the entering rows take their g from a block of 32 loaded a
+    // block ahead (a load issued inside the panel step would be waited for right away: the scoreboard is per warp)
+    double gv = (lane < NA) ? g[lane] : 0.0;
+    double gcur = (32 + lane < NA) ? g[32 + lane] : 0.0;
+    double gnext = (64 + lane < NA) ? g[64 + lane] : 0.0;
     bool ok = true;
     if (lane == 0) {
-        for (int t = 0; t < 2 && t < nunits; ++t) {
-            const unsigned hs = (tick + t) % HB_SLOTS;
-            mbar_expect_tx(&sh.hb_full[hs], HB_UNIT_BYTES);
-            tma_load_1d(sh.u.f.hb[hs], F.HB + (size_t)t * SUB * HB_PITCH, HB_UNIT_BYTES, &sh.hb_full[hs], pol);
-        }
+        mbar_expect_tx(&sh.hb_full[tick % HB_SLOTS], HB_UNIT_BYTES);
+        tma_load_1d(sh.u.f.hb[tick % HB_SLOTS], HBp, HB_UNIT_BYTES, &sh.hb_full[tick % HB_SLOTS], pol);
     }
+    SEG_BEGIN();
     for (int t = 0; t < nunits; ++t) {
-        const unsigned ht = tick + t, hs = ht % HB_SLOTS, ls = ht % LT_SLOTS;
-        if (lane == 0 && t + 2 < nunits) {            // slot of unit t-1: every lane has passed that unit's last __syncwarp
-            const unsigned h2 = (ht + 2) % HB_SLOTS;
-            mbar_expect_tx(&sh.hb_full[h2], HB_UNIT_BYTES);
-            tma_load_1d(sh.u.f.hb[h2], F.HB + (size_t)(t + 2) * SUB * HB_PITCH, HB_UNIT_BYTES, &sh.hb_full[h2], pol);
-        }
-        mbar_wait(&sh.hb_full[hs], (ht / HB_SLOTS) & 1u);
-        if (ht >= (unsigned)LT_SLOTS) mbar_wait(&sh.lt_empty[ls], ((ht / LT_SLOTS) - 1u) & 1u);
-        const double *hbg = sh.u.f.hb[hs];
-        double *ltg = sh.u.f.lt[ls];
+        const unsigned ht = tick + t, hs = ht % HB_SLOTS, ls = ht % HO_SLOTS;
         const int k0 = t * SUB;
-        const int nst = min(SUB, NA - k0);
-        int rho = (lane - k0 - 1) & 31;               // this lane's row is k + 1 + rho; rho == 31: the row k + 32 enters
-        double a_cur = hbg[1 + rho], pd_cur = hbg[HB_PITCH - 1];
-#pragma unroll 1
-        for (int s = 0; s < nst; ++s) {
-            const int k = k0 + s;
-            const bool isk = (rho == 31);             // lane == k & 31: holds the pivot row k and receives row k + 32
-            const double a = (k + 1 + rho < NA) ? a_cur : 0.0;
-            const double t0 = (isk ? pd_cur : a) - acc[0];
-            const double v = isk ? a : t0;            // (the entering row has no updates yet)
-            double *cb = sh.cb[k & 1];
-            cb[rho] = v;
-            if (isk) *reinterpret_cast<double2 *>(&cb[32]) = make_double2(t0, gk - gacc);
-            __syncwarp();
-            if (s + 1 < nst) {                        // band entries of the next column (off the pivot chain)
-                a_cur = hbg[(s + 1) * HB_PITCH + 1 + ((rho - 1) & 31)];
-                pd_cur = hbg[(s + 1) * HB_PITCH + HB_PITCH - 1];
-            }
-            const double2 dy = *reinterpret_cast<const double2 *>(&cb[32]);
-            if (!(dy.x > 0.0)) ok = false;
-            const double w = fast_rcp(dy.x);
-            const double lm = v * w;
-            const int m = isk ? 0 : -1;
-            // the window slides by one column: acc[c] <- acc[c+1] + l v_c   (slot c: column k + 1 + c)
+        SEG(8);
+        if (t > 0 && (t & 3) == 0) {                  // a new block of 32 rows enters over the next four panels
+            gcur = gnext;
+            const int idx = k0 + 64 + lane;
+            gnext = (idx < NA) ? g[idx] : 0.0;
+        }
+        if (lane == 0 && t + 1 < nunits) {            // band rows of the next panel (slot of panel t-1: all lanes are past it)
+            const unsigned h2 = (ht + 1) % HB_SLOTS;
+            mbar_expect_tx(&sh.hb_full[h2], HB_UNIT_BYTES);
+            tma_load_1d(sh.u.f.hb[h2], HBp + (size_t)(t + 1) * SUB * HB_PITCH, HB_UNIT_BYTES, &sh.hb_full[h2], pol);
+        }
+        PROF_T0(tw1);
+        if (ht >= (unsigned)HO_SLOTS) mbar_wait(&sh.ho_empty[ls], ((ht / HO_SLOTS) - 1u) & 1u);
+        PROF_ADD(19, tw1);
+        Handoff &ho = sh.u.f.ho[ls];
+        SEG(9);
+        // ---- (1) block column 0 of the window -> row layout, through the (still free) fragment area of the hand-off slot
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-                const double2 cc = *reinterpret_cast<const double2 *>(&cb[c]);
-                acc[c] = fma(lm, cc.x, mask_hi(acc[c + 1], m));
-                if (c + 2 < 32) acc[c + 1] = fma(lm, cc.y, mask_hi(acc[c + 2], m));
-                else acc[c + 1] = lm * cc.y;          // column k + 32 enters the window
+        for (int I = 0; I < 4; ++I)
+            *reinterpret_cast<double2 *>(&ho.vb[(8 * I + gq) * VBP + 2 * q]) = make_double2(W[blk(I, 0)][0], W[blk(I, 0)][1]);
+        __syncwarp();
+        double p[8], p2[8];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            const double2 uu = *reinterpret_cast<const double2 *>(&ho.vb[lane * VBP + j]);
+            p[j] = uu.x; p[j + 1] = uu.y;
+        }
+        PROF_T0(tw0);
+        mbar_wait(&sh.hb_full[hs], (ht / HB_SLOTS) & 1u);
+        PROF_ADD(14, tw0);
+        const double *hbg = sh.u.f.hb[hs];
+        const bool row_ok = (k0 + lane < NA), row2_ok = (lane < 8) && (k0 + 32 + lane < NA);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int d = lane - j;                    // row k0 + lane, column k0 + j: band entry H[k0+j][d]; d = 0: the pivot (with D)
+            const bool col_ok = (k0 + j < NA);
+            double a1 = 0.0;
+            if (d >= 0 && row_ok && col_ok) a1 = hbg[j * HB_PITCH + ((d == 0) ? HB_PITCH - 1 : d)];
+            if (d == 0 && !col_ok) a1 = 1.0;           // padding column: unit pivot
+            p[j] = (d >= 0) ? a1 - p[j] : 0.0;
+            const int d2 = 32 + lane - j;              // entering row k0 + 32 + lane: nonzero for j >= lane only, no updates yet
+            p2[j] = (row2_ok && col_ok && d2 <= 32) ? hbg[j * HB_PITCH + d2] : 0.0;
+        }
+        double gv2 = __shfl_sync(FULL, gcur, ((t & 3) << 3) + (lane & 7));
+        if (lane >= 8) gv2 = 0.0;
+        __syncwarp();                                  // every lane has read its row of block column 0: the slot can take L now
+        SEG(10);
+        // ---- (2) the panel ----
+        double dsave = 1.0, wsave = 1.0, ysave = 0.0;
+        double *ltp = LTp + (size_t)k0 * FROW;
+        const int wr = (lane >= 8) ? lane - 8 : 24 + lane;      // window row (after the slide) of the row this lane hands over
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double dj = __shfl_sync(FULL, p[j], j);
+            const double yj = __shfl_sync(FULL, gv, j);
+            if (!(dj > 0.0)) ok = false;
+            const double w = fast_rcp(dj);
+            const double lt = p[j] * w, lt2 = p2[j] * w;           // (lanes <= j: lt is not an entry of L; lanes > j: lt2 = 0)
+            // column k0 + j of L: lane l > j holds row k0 + l (offset l - j - 1), lane l <= j the entering row (offset 31 + l - j)
+            __stcs(ltp + j * FROW + ((lane - j - 1) & 31), (lane > j) ? lt : lt2);
+            ho.vb[wr * VBP + j] = (lane >= 8) ? lt : lt2;
+            if (lane < 8 && lane > j) ho.l11[lane * 8 + j] = lt;
+            if (lane == j) { dsave = dj; wsave = w; ysave = yj; }
+            gv = fma(-lt, yj, gv);                                 // (lanes <= j: gv is dead)
+            gv2 = fma(-lt2, yj, gv2);
+#pragma unroll
+            for (int jj = j + 1; jj < 8; ++jj) {
+                const double vj = __shfl_sync(FULL, p[j], jj);     // v of row k0 + jj in column j (unscaled)
+                p[jj] = fma(-lt, vj, p[jj]);
+                p2[jj] = fma(-lt2, vj, p2[jj]);
             }
-            gacc = fma(lm, dy.y, isk ? 0.0 : gacc);
-            // the column: to the fill warp (shared) and to the slab (HBM)
-            ltg[s * LTS + rho] = lm;
-            __stcs(&F.LT[(size_t)k * LTG + rho], lm);
-            if (isk) {
-                *reinterpret_cast<double2 *>(&ltg[s * LTS + 32]) = make_double2(w, dy.y);
-                F.WP[k] = w;
-                F.YP[k] = dy.y;
-                gk = (k + 32 < NA) ? g[k + 32] : 0.0;
-            }
-            rho = (rho - 1) & 31;
+        }
+        SEG(11);
+        if (lane < 8) {
+            ho.w[lane] = wsave;
+            ho.y[lane] = ysave;
+            __stcs(ltp + lane * FROW + 33, wsave);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sh.lt_full[ls]);
+        // ---- (3) trailing update on the tensor cores; the window slides by one block ----
+        double af[4][2], bf[4][2];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const double dk = __shfl_sync(FULL, dsave, 4 * ks + q);
+#pragma unroll
+            for (int I = 0; I < 4; ++I) {
+                bf[I][ks] = ho.vb[(8 * I + gq) * VBP + 4 * ks + q];
+                af[I][ks] = bf[I][ks] * dk;
+            }
+        }
+#pragma unroll
+        for (int I = 0; I < 4; ++I)
+#pragma unroll
+            for (int J = 0; J <= I; ++J) {
+                double c[2] = {0.0, 0.0};
+                if (I < 3) { c[0] = W[blk(I + 1, J + 1)][0]; c[1] = W[blk(I + 1, J + 1)][1]; }
+                dmma(c, af[I][0], bf[J][0]);
+                dmma(c, af[I][1], bf[J][1]);
+                W[blk(I, J)][0] = c[0]; W[blk(I, J)][1] = c[1];
+            }
+        // rows slide by eight as well
+        {
+            const double up = __shfl_sync(FULL, gv, (lane + 8) & 31), en = __shfl_sync(FULL, gv2, (lane - 24) & 31);
+            gv = (lane < 24) ? up : en;
+        }
+        __syncwarp();
+        SEG(12);
+        if (lane == 0) mbar_arrive(&sh.ho_full[ls]);
     }
     return ok;
 }
 
-// ---- warp 1: fill row G = Y L^-T (lane = separator row), S -= (G w) G^T, and the separator part of the fused forward
-//      substitution  gS -= G (w y) ----
-__device__ __noinline__ void factor_fill(IpShared &sh, const Factor F, const double *__restrict__ g, unsigned tick) {
+// ---- warp 1: fill rows G = Y L^-T (lane = separator row), blocked like the chain: the 32 x 32 window of G's updates in
+//      DMMA C fragments, panel by forward substitution with the panel's unit-lower block, trailing update
+//      G'[:, J] = G[:, J+1] + G_panel L^T and S -= (G_panel w) G_panel^T on the tensor cores; also the separator part of
+//      the fused forward substitution  gS -= G (w y) ----
+__device__ __noinline__ void factor_fill(IpShared &sh, const double *__restrict__ HBp, double *__restrict__ LTp, double *__restrict__ GTp, const int NA, const double *__restrict__ g, unsigned tick) {
     const int lane = threadIdx.x & 31;
     const int gq = lane >> 2, q = lane & 3;
-    const int NA = F.NA;
     const int nunits = (NA + SUB - 1) / SUB;
-    double facc[32];
+    double G[4][4][2];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) facc[c] = 0.0;
+    for (int I = 0; I < 4; ++I)
+#pragma unroll
+        for (int J = 0; J < 4; ++J) { G[I][J][0] = 0.0; G[I][J][1] = 0.0; }
     double gsacc = 0.0;
+    double *gb = sh.u.f.gb;
     for (int t = 0; t < nunits; ++t) {
-        const unsigned ht = tick + t, ls = ht % LT_SLOTS;
-        mbar_wait(&sh.lt_full[ls], (ht / LT_SLOTS) & 1u);
-        const double *ltg = sh.u.f.lt[ls];
+        const unsigned ht = tick + t, ls = ht % HO_SLOTS;
         const int k0 = t * SUB;
-        const int nst = min(SUB, NA - k0);
-        const bool hasY = (k0 < 32) || (k0 + SUB - 1 >= NA - 32);     // Y = M[sep, chain] is nonzero across the wrap and next to the separator
-#pragma unroll 1
-        for (int s = 0; s < nst; ++s) {
-            const int k = k0 + s;
-            const double *col = ltg + s * LTS;
-            double yv = 0.0;
-            if (hasY) {
-                if (k <= lane) yv = F.HB[(size_t)(NA + lane) * HB_PITCH + (k + 32 - lane)];
-                else if (k >= NA + lane - 32) yv = F.HB[(size_t)k * HB_PITCH + (NA + lane - k)];
-            }
-            const double gv = yv - facc[0];
-            sh.u.f.gt[s * GTS + lane] = gv;
-            __stcs(&F.GT[(size_t)k * GTS + lane], gv);
-            const double2 wy = *reinterpret_cast<const double2 *>(&col[32]);
-            gsacc = fma(gv, wy.x * wy.y, gsacc);
-            // the window slides by one column: facc[c] <- facc[c+1] + g l_c   (slot c: column k + 1 + c)
+        // ---- column block 0 of the window -> row layout ----
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-                const double2 cc = *reinterpret_cast<const double2 *>(&col[c]);
-                facc[c] = fma(gv, cc.x, facc[c + 1]);
-                if (c + 2 < 32) facc[c + 1] = fma(gv, cc.y, facc[c + 2]);
-                else facc[c + 1] = gv * cc.y;         // column k + 32 enters the window
-            }
+        for (int I = 0; I < 4; ++I)
+            *reinterpret_cast<double2 *>(&gb[(8 * I + gq) * VBP + 2 * q]) = make_double2(G[I][0][0], G[I][0][1]);
+        __syncwarp();
+        double gp[8];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            const double2 uu = *reinterpret_cast<const double2 *>(&gb[lane * VBP + j]);
+            gp[j] = uu.x; gp[j + 1] = uu.y;
         }
-        if (nst < SUB) {
-            for (int s = nst; s < SUB; ++s) sh.u.f.gt[s * GTS + lane] = 0.0;
+        const bool hasY = (k0 < 32) || (k0 + SUB - 1 >= NA - 32);     // Y = M[sep, chain] is nonzero across the wrap and next to the separator
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + j;
+            double yv = 0.0;
+            if (hasY && k < NA) {
+                if (k <= lane) yv = HBp[(size_t)(NA + lane) * HB_PITCH + (k + 32 - lane)];
+                else if (k >= NA + lane - 32) yv = HBp[(size_t)k * HB_PITCH + (NA + lane - k)];
+            }
+            gp[j] = yv - gp[j];
         }
         __syncwarp();
-        // ---- S -= (G w) G^T over the unit's columns: lower 8x8 blocks (I >= J) on the tensor cores ----
-#pragma unroll 1
+        PROF_T0(tw2);
+        mbar_wait_relaxed(&sh.ho_full[ls], (ht / HO_SLOTS) & 1u);
+        PROF_ADD1(20, tw2);
+        const Handoff &ho = sh.u.f.ho[ls];
+        // ---- the panel: g_j -= sum_{m<j} g_m L[k0+j][k0+m] ----
+#pragma unroll
+        for (int m = 0; m < 7; ++m)                 // right-looking: gp[m] is final, the updates of one column are independent
+#pragma unroll
+            for (int j = m + 1; j < 8; ++j) gp[j] = fma(-gp[m], ho.l11[j * 8 + m], gp[j]);
+        double *gtp = GTp + (size_t)k0 * FROW;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            __stcs(gtp + j * FROW + lane, gp[j]);
+            gsacc = fma(gp[j], ho.w[j] * ho.y[j], gsacc);
+        }
+        if (lane < 8) {
+            const double w = ho.w[lane];
+            *reinterpret_cast<double2 *>(gtp + lane * FROW + 32) = make_double2(w * ho.y[lane], w);      // [z, w]
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2 *>(&gb[lane * VBP + j]) = make_double2(gp[j], gp[j + 1]);
+        __syncwarp();
+        PROF_T0(tw3);
+        // ---- trailing update: G'[I][J] = G[I][J+1] + G_panel[I] L[J]^T ----
+        double af[4][2], bf[4][2], wq[2];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            wq[ks] = ho.w[4 * ks + q];
+#pragma unroll
+            for (int I = 0; I < 4; ++I) {
+                af[I][ks] = gb[(8 * I + gq) * VBP + 4 * ks + q];
+                bf[I][ks] = ho.vb[(8 * I + gq) * VBP + 4 * ks + q];
+            }
+        }
+#pragma unroll
+        for (int I = 0; I < 4; ++I)
+#pragma unroll
+            for (int J = 0; J < 4; ++J) {
+                double c[2] = {0.0, 0.0};
+                if (J < 3) { c[0] = G[I][J + 1][0]; c[1] = G[I][J + 1][1]; }
+                dmma(c, af[I][0], bf[J][0]);
+                dmma(c, af[I][1], bf[J][1]);
+                G[I][J][0] = c[0]; G[I][J][1] = c[1];
+            }
+        // ---- S += (G_panel w) G_panel^T (lower blocks; subtracted from M[sep, sep] at the end) ----
+#pragma unroll
         for (int I = 0; I < 4; ++I) {
-            double a[2];
+            double c2[4][2];
+#pragma unroll
+            for (int J = 0; J <= I; ++J) {
+                c2[J][0] = sh.s.sfrag[(2 * blk(I, J)) * 32 + lane];
+                c2[J][1] = sh.s.sfrag[(2 * blk(I, J) + 1) * 32 + lane];
+            }
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-                const int kk = 4 * ks + q;
-                const double wq = (kk < nst) ? ltg[kk * LTS + 32] : 0.0;
-                a[ks] = sh.u.f.gt[kk * GTS + 8 * I + gq] * wq;
-            }
-#pragma unroll 1
-            for (int J = 0; J <= I; ++J) {
-                const int bi = (I * (I + 1)) / 2 + J;
-                double c2[2];
-                c2[0] = sh.s.sfrag[(2 * bi) * 32 + lane];
-                c2[1] = sh.s.sfrag[(2 * bi + 1) * 32 + lane];
+                const double a = af[I][ks] * wq[ks];
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) dmma(c2, a[ks], sh.u.f.gt[(4 * ks + q) * GTS + 8 * J + gq]);
-                sh.s.sfrag[(2 * bi) * 32 + lane] = c2[0];
-                sh.s.sfrag[(2 * bi + 1) * 32 + lane] = c2[1];
+                for (int J = 0; J <= I; ++J) dmma(c2[J], a, af[J][ks]);
+            }
+#pragma unroll
+            for (int J = 0; J <= I; ++J) {
+                sh.s.sfrag[(2 * blk(I, J)) * 32 + lane] = c2[J][0];
+                sh.s.sfrag[(2 * blk(I, J) + 1) * 32 + lane] = c2[J][1];
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sh.lt_empty[ls]);
+        PROF_ADD1(21, tw3);
+        if (lane == 0) mbar_arrive(&sh.ho_empty[ls]);
     }
     sh.gs[lane] = g[NA + lane] - gsacc;
 }
@@ -314,28 +458,41 @@ __device__ __noinline__ bool factor(IpShared &sh, double *slab, const Layout &L,
     const int NA = F.NA;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *HBw = slab + L.o_hb;
+#pragma unroll 4
     for (int i = threadIdx.x; i < NA; i += IP_THREADS) HBw[(size_t)i * HB_PITCH + HB_PITCH - 1] = HBw[(size_t)i * HB_PITCH] + F.DD[i];
     for (int e = threadIdx.x; e < 20 * 32; e += IP_THREADS) sh.s.sfrag[e] = 0.0;
     fence_proxy_async();        // the pivots above (generic proxy) are read by the bulk copies (async proxy)
     __syncthreads();
+    PROF_T0(tc0);
     if (warp == 0) {
-        if (!factor_chain(sh, F, g, tick)) sh.flag = 1;
+        if (!factor_chain(sh, F.HB, F.LT, F.GT, NA, g, tick)) sh.flag = 1;
+        PROF_ADD(1, tc0);
     } else {
-        factor_fill(sh, F, g, tick);
+        factor_fill(sh, F.HB, F.LT, F.GT, NA, g, tick);
+        PROF_ADD1(13, tc0);
     }
+    PROF_T0(tc1);
     // ---- separator: S = M[sep, sep] + D_S - G D^-1 G^T, LDL^T in place (warp 1) ----
     double sf[20];
     if (warp == 1) {
 #pragma unroll
         for (int e = 0; e < 20; ++e) sf[e] = sh.s.sfrag[e * 32 + lane];
     }
-    __syncthreads();
-    for (int e = threadIdx.x; e < 1024; e += IP_THREADS) {
+    // (the separator block of M: 16 entries per thread, all loads in flight before the barrier)
+    double sv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int e = threadIdx.x + i * IP_THREADS;
         const int r = e >> 5, c = e & 31;
         const int lo = min(r, c), dist = abs(r - c);
-        double v = F.HB[(size_t)(NA + lo) * HB_PITCH + dist];
-        if (r == c) v += F.DD[NA + r];
-        sh.s.Ss[r * 33 + c] = v;
+        sv[i] = F.HB[(size_t)(NA + lo) * HB_PITCH + dist];
+        if (r == c) sv[i] += F.DD[NA + r];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int e = threadIdx.x + i * IP_THREADS;
+        sh.s.Ss[(e >> 5) * 33 + (e & 31)] = sv[i];
     }
     __syncthreads();
     if (warp == 1) {
@@ -353,26 +510,29 @@ __device__ __noinline__ bool factor(IpShared &sh, double *slab, const Layout &L,
                 }
             }
         __syncwarp();
+        // right-looking LDL^T with this lane's row in registers (full square, like the chain: no masks)
         bool ok = true;
-        double *row = sh.s.Ss + lane * 33;
-#pragma unroll 1
+        double row[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) row[c] = sh.s.Ss[lane * 33 + c];
+#pragma unroll
         for (int k = 0; k < 32; ++k) {
-            const double v = row[k];
             double *cb = sh.part[k & 1];
-            cb[lane] = v;
+            cb[lane] = row[k];
             __syncwarp();
             const double d = cb[k];
             if (!(d > 0.0)) ok = false;
             const double w = fast_rcp(d);
-            const double l = v * w;
-#pragma unroll 4
+            const double l = row[k] * w;
+#pragma unroll
             for (int c = k + 1; c < 32; ++c) row[c] = fma(-l, cb[c], row[c]);
-            if (lane > k) row[k] = l;
+            if (lane > k) sh.s.Ss[lane * 33 + k] = l;
             if (lane == k) sh.wS[k] = w;
         }
         if (!ok) sh.flag = 1;
     }
     __syncthreads();
+    PROF_ADD(5, tc1);
     return sh.flag == 0;
 }
 
@@ -382,104 +542,137 @@ struct Ring {
     unsigned phase;
     uint64_t pol;
     __device__ Ring(IpShared &s) : sh(s), phase(s.ring_phase), pol(l2_evict_first_policy()) {}
-    __device__ __forceinline__ void issue(int unit, const double *src, unsigned bytes) {
+    __device__ __forceinline__ void issue(int unit, const double *rows) {
         const int sl = unit % RING_UNITS;
-        mbar_expect_tx(&sh.ring_full[sl], bytes);
-        tma_load_1d(sh.u.ring[sl], src, bytes, &sh.ring_full[sl], pol);
+        mbar_expect_tx(&sh.ring_full[sl], FUNIT_BYTES);
+        tma_load_1d(sh.u.ring[sl], rows + (size_t)unit * SUB * FROW, FUNIT_BYTES, &sh.ring_full[sl], pol);
     }
     __device__ __forceinline__ const double *wait(int unit) {
         const int sl = unit % RING_UNITS;
+#ifdef MC_PROFILE
+        const long long tw = clock64();
+#endif
         mbar_wait(&sh.ring_full[sl], (phase >> sl) & 1u);
+#ifdef MC_PROFILE
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&g_prof[22 + (threadIdx.x >> 5)], (unsigned long long)(clock64() - tw));
+#endif
         phase ^= 1u << sl;
         return sh.u.ring[sl];
     }
     __device__ __forceinline__ void close() { sh.ring_phase = phase; }
 };
 
-// forward sweep (warp 0): y = L^-1 g, right-looking; lane = row (circular)
-__device__ __noinline__ void sweep_forward(IpShared &sh, const Factor F, const double *__restrict__ g) {
+// forward sweep (warp 0): y = L^-1 g, one panel of eight columns at a time.  lane l = row k0 + l (lanes 0..7 also carry the
+// entering row k0 + 32 + l).  The panel's 8x8 unit-lower solve is done redundantly by every lane from broadcast loads (a
+// chain of dependent DFMAs, no shuffle in it), then each lane updates its own row with eight DFMAs.
+// z = w y goes into the fill rows (GT[k][32]) for the separator's part of the substitution.
+__device__ __noinline__ void sweep_forward(IpShared &sh, const double *__restrict__ HBp, double *__restrict__ LTp, double *__restrict__ GTp, const int NA, const double *__restrict__ g) {
     const int lane = threadIdx.x & 31;
-    const int NA = F.NA;
     const int nunits = (NA + SUB - 1) / SUB;
     Ring R(sh);
     if (lane == 0)
-        for (int u = 0; u < 3 && u < nunits; ++u) R.issue(u, F.LT + (size_t)u * SUB * LTG, LT_UNIT_BYTES);
+        for (int u = 0; u < 6 && u < nunits; ++u) R.issue(u, LTp);
     double acc = (lane < NA) ? g[lane] : 0.0;
-    double gk = (lane + 32 < NA) ? g[lane + 32] : 0.0;
+    double gcur = (32 + lane < NA) ? g[32 + lane] : 0.0;       // g of the rows that enter over the next four panels,
+    double gnext = (64 + lane < NA) ? g[64 + lane] : 0.0;      // and the block after it (loaded a block ahead)
     for (int u = 0; u < nunits; ++u) {
+        const int k0 = u * SUB;
+        if (u > 0 && (u & 3) == 0) {
+            gcur = gnext;
+            const int idx = k0 + 64 + lane;
+            gnext = (idx < NA) ? g[idx] : 0.0;
+        }
         const double *lt = R.wait(u);
-        const int k0 = u * SUB, nst = min(SUB, NA - k0);
-        int rho = (lane - k0 - 1) & 31;
-        double l[SUB];
+        double acc2 = __shfl_sync(FULL, gcur, ((u & 3) << 3) + (lane & 7));
+        if (lane >= 8) acc2 = 0.0;
+        // this lane's entries of the eight columns: row k0 + l for l > j, the entering row for l <= j
+        double la[8], lb[8];
 #pragma unroll
-        for (int s = 0; s < SUB; ++s) l[s] = lt[s * LTG + ((rho - s) & 31)];
+        for (int j = 0; j < 8; ++j) {
+            const double l = lt[j * FROW + ((lane - j - 1) & 31)];
+            la[j] = (lane > j) ? l : 0.0;
+            lb[j] = (lane > j) ? 0.0 : l;
+        }
+        const double wl = lt[(lane & 7) * FROW + 33];
+        double l11[28];                            // the panel's unit-lower block L[k0+m][k0+j], m > j: all loads before the chain
 #pragma unroll
-        for (int s = 0; s < SUB; ++s) {
-            if (s < nst) {
-                const int k = k0 + s;
-                const double yk = __shfl_sync(FULL, acc, k & 31);
-                if (lane == (k & 31)) {
-                    F.YP[k] = yk;
-                    acc = fma(-l[s], yk, gk);
-                    gk = (k + 64 < NA) ? g[k + 64] : 0.0;
-                } else {
-                    acc = fma(-l[s], yk, acc);
-                }
+        for (int j = 0; j < 7; ++j)
+#pragma unroll
+            for (int m = j + 1; m < 8; ++m) l11[(m * (m - 1)) / 2 + j] = lt[j * FROW + (m - j - 1)];
+        double y[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) y[m] = __shfl_sync(FULL, acc, m);
+#pragma unroll
+        for (int j = 0; j < 7; ++j)                 // right-looking: y[j] is final, the updates of one column are independent
+#pragma unroll
+            for (int m = j + 1; m < 8; ++m) y[m] = fma(-l11[(m * (m - 1)) / 2 + j], y[j], y[m]);
+        {
+            double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;       // two partial sums per row: half the dependent chain
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                e0 = fma(la[j], y[j], e0); e1 = fma(la[j + 1], y[j + 1], e1);
+                f0 = fma(lb[j], y[j], f0); f1 = fma(lb[j + 1], y[j + 1], f1);
             }
+            acc -= e0 + e1;                         // (lanes 0..7 end up with their own y)
+            acc2 -= f0 + f1;
+        }
+        if (lane < 8 && k0 + lane < NA) GTp[(size_t)(k0 + lane) * FROW + 32] = acc * wl;
+        {
+            const double up = __shfl_sync(FULL, acc, (lane + 8) & 31), en = __shfl_sync(FULL, acc2, (lane - 24) & 31);
+            acc = (lane < 24) ? up : en;
         }
         __syncwarp();
-        if (lane == 0 && u + 3 < nunits) R.issue(u + 3, F.LT + (size_t)(u + 3) * SUB * LTG, LT_UNIT_BYTES);
+        if (lane == 0 && u + 6 < nunits) R.issue(u + 6, LTp);
     }
     R.close();
+    fence_proxy_async();        // z (generic-proxy stores) is read back through bulk copies (async proxy)
 }
 
-// separator part of the forward sweep (warp 1):  gs = g_S - G (w y)
-__device__ __noinline__ void sweep_sep_rhs(IpShared &sh, const Factor F, const double *__restrict__ g) {
+// separator part of the forward sweep (warp 1):  gs = g_S - G z
+__device__ __noinline__ void sweep_sep_rhs(IpShared &sh, const double *__restrict__ HBp, double *__restrict__ LTp, double *__restrict__ GTp, const int NA, const double *__restrict__ g) {
     const int lane = threadIdx.x & 31;
-    const int NA = F.NA;
     const int nunits = (NA + SUB - 1) / SUB;
     Ring R(sh);
     if (lane == 0)
-        for (int u = 0; u < 4 && u < nunits; ++u) R.issue(u, F.GT + (size_t)u * SUB * GTS, GT_UNIT_BYTES);
+        for (int u = 0; u < 6 && u < nunits; ++u) R.issue(u, GTp);
     double s0 = 0.0, s1 = 0.0;
+    const double gsl = g[NA + lane];
     for (int u = 0; u < nunits; ++u) {
-        const int k0 = u * SUB, nst = min(SUB, NA - k0);
-        const int kk = k0 + (lane & 7);
-        const double zl = (kk < NA) ? F.YP[kk] * F.WP[kk] : 0.0;      // lanes 0..7 (replicated): z of the unit's columns
+        const int nst = min(SUB, NA - u * SUB);
         const double *gt = R.wait(u);
 #pragma unroll
         for (int s = 0; s < SUB; s += 2) {
-            const double z0 = __shfl_sync(FULL, zl, s), z1 = __shfl_sync(FULL, zl, s + 1);
-            if (s < nst) s0 = fma(gt[s * GTS + lane], z0, s0);
-            if (s + 1 < nst) s1 = fma(gt[(s + 1) * GTS + lane], z1, s1);
+            if (s < nst) s0 = fma(gt[s * FROW + lane], gt[s * FROW + 32], s0);
+            if (s + 1 < nst) s1 = fma(gt[(s + 1) * FROW + lane], gt[(s + 1) * FROW + 32], s1);
         }
         __syncwarp();
-        if (lane == 0 && u + 4 < nunits) R.issue(u + 4, F.GT + (size_t)(u + 4) * SUB * GTS, GT_UNIT_BYTES);
+        if (lane == 0 && u + 6 < nunits) R.issue(u + 6, GTp);
     }
     R.close();
-    sh.gs[lane] = g[NA + lane] - (s0 + s1);
+    sh.gs[lane] = gsl - (s0 + s1);
 }
 
 // separator solve and the right-hand side of the backward sweep (warp 1):
-//   x_S = S^-1 gs;   t = (y - G^T x_S) w
-__device__ __noinline__ void sweep_sep_solve(IpShared &sh, const Factor F, double *__restrict__ x) {
+//   x_S = S^-1 gs;   t = (y - G^T x_S) w = z - w G^T x_S   -> LT[k][32]
+__device__ __noinline__ void sweep_sep_solve(IpShared &sh, const double *__restrict__ HBp, double *__restrict__ LTp, double *__restrict__ GTp, const int NA, double *__restrict__ x) {
     const int lane = threadIdx.x & 31;
-    const int NA = F.NA;
     const int nunits = (NA + SUB - 1) / SUB;
     Ring R(sh);
     if (lane == 0)
-        for (int u = 0; u < 4 && u < nunits; ++u) R.issue(u, F.GT + (size_t)u * SUB * GTS, GT_UNIT_BYTES);
+        for (int u = 0; u < 6 && u < nunits; ++u) R.issue(u, GTp);
     double a = sh.gs[lane];
-#pragma unroll 4
+#pragma unroll
     for (int k = 0; k < 32; ++k) {
         const double yk = __shfl_sync(FULL, a, k);
-        if (lane > k) a = fma(-sh.s.Ss[lane * 33 + k], yk, a);
+        const double l = (lane > k) ? sh.s.Ss[lane * 33 + k] : 0.0;
+        a = fma(-l, yk, a);
     }
     a *= sh.wS[lane];
-#pragma unroll 4
+#pragma unroll
     for (int k = 31; k >= 0; --k) {
         const double xk = __shfl_sync(FULL, a, k);
-        if (lane < k) a = fma(-sh.s.Ss[k * 33 + lane], xk, a);
+        const double l = (lane < k) ? sh.s.Ss[k * 33 + lane] : 0.0;
+        a = fma(-l, xk, a);
     }
     x[NA + lane] = a;
     // c_k = sum_r G[r][k] x_S[r]: lane = (column k0 + (lane & 7), quarter lane >> 3 of the separator rows)
@@ -489,55 +682,104 @@ __device__ __noinline__ void sweep_sep_solve(IpShared &sh, const Factor F, doubl
     for (int i = 0; i < 8; ++i) xq[i] = __shfl_sync(FULL, a, 8 * qr + i);
     for (int u = 0; u < nunits; ++u) {
         const int k = u * SUB + kl;
-        const double yk = (k < NA) ? F.YP[k] : 0.0, wk = (k < NA) ? F.WP[k] : 0.0;
-        const double *gt = R.wait(u) + kl * GTS + 8 * qr;
-        double c = 0.0;
+        const double *gt = R.wait(u) + kl * FROW;
+        const double2 zw = *reinterpret_cast<const double2 *>(&gt[32]);
+        double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) c = fma(gt[i], xq[i], c);
+        for (int i = 0; i < 8; i += 2) {
+            const double2 gg = *reinterpret_cast<const double2 *>(&gt[8 * qr + i]);
+            c0 = fma(gg.x, xq[i], c0);
+            c1 = fma(gg.y, xq[i + 1], c1);
+        }
+        double c = c0 + c1;
         c += __shfl_xor_sync(FULL, c, 8);
         c += __shfl_xor_sync(FULL, c, 16);
-        if (qr == 0 && k < NA) F.TP[k] = (yk - c) * wk;
+        if (qr == 0 && k < NA) LTp[(size_t)k * FROW + 32] = fma(-c, zw.y, zw.x);
         __syncwarp();
-        if (lane == 0 && u + 4 < nunits) R.issue(u + 4, F.GT + (size_t)(u + 4) * SUB * GTS, GT_UNIT_BYTES);
+        if (lane == 0 && u + 6 < nunits) R.issue(u + 6, GTp);
     }
     R.close();
+    fence_proxy_async();        // t (generic-proxy stores) is read back through bulk copies (async proxy)
 }
 
-// backward sweep (warp 0): x = L^-T t, right-looking from the last column; lane = row (circular).  Step k needs row k of
-// L, i.e. the entries LT[j][k-1-j] of the 32 columns before k: five resident units + two in flight.
-__device__ __noinline__ void sweep_backward(IpShared &sh, const Factor F, double *__restrict__ x) {
+// backward sweep (warp 0): x = L^-T t, one panel at a time from the last one.  Before panel k0 lane l holds the
+// accumulator of row k0 - 24 + l (the panel's rows are lanes 24..31), lanes 0..7 also the entering row k0 - 32 + l.
+// The panel's 8x8 unit-upper solve is done redundantly by every lane from broadcast loads; each row then takes the eight
+// entries L[k0+m][row] = LT[row][k0+m-row-1] it needs from its own (resident) factor row: five units resident, two in flight.
+__device__ __noinline__ void sweep_backward(IpShared &sh, const double *__restrict__ HBp, double *__restrict__ LTp, double *__restrict__ GTp, const int NA, double *__restrict__ x) {
     const int lane = threadIdx.x & 31;
-    const int NA = F.NA;
     const int nunits = (NA + SUB - 1) / SUB;
+    SEG_BEGIN();
     Ring R(sh);
     const int U0 = nunits - 1;
+    SEG(16);
     if (lane == 0)
-        for (int u = U0; u > U0 - 6 && u >= 0; --u) R.issue(u, F.LT + (size_t)u * SUB * LTG, LT_UNIT_BYTES);
-    for (int u = U0; u > U0 - 4 && u >= 0; --u) R.wait(u);            // (units U0 .. U0-3; U-4 is waited per unit below)
-    int row = NA - 1 - ((NA - 1 - lane) & 31);                        // the row == lane (mod 32) among the last 32
-    double acc = (row >= 0) ? F.TP[row] : 0.0;
-    double tk = (row - 32 >= 0) ? F.TP[row - 32] : 0.0;
+        for (int u = U0; u > U0 - 6 && u >= 0; --u) R.issue(u, LTp);
+    SEG(17);
+    for (int u = U0; u > U0 - 4 && u >= 0; --u) R.wait(u);            // rows k0 - 24 .. k0 + 7 of the first panel
+    SEG(18);
+    double acc;
+    {
+        const int r1 = U0 * SUB - 24 + lane;
+        acc = (r1 >= 0 && r1 < NA) ? sh.u.ring[(r1 >> 3) % RING_UNITS][(r1 & 7) * FROW + 32] : 0.0;     // t of the row
+    }
+    SEG(19);
     for (int U = U0; U >= 0; --U) {
+        const int k0 = U * SUB;
+        SEG(0);
         if (U - 4 >= 0) R.wait(U - 4);
-        const int khi = min(NA - 1, U * SUB + SUB - 1);
-#pragma unroll 2
-        for (int k = khi; k >= U * SUB; --k) {
-            const int kap = k & 31;
-            const double xk = __shfl_sync(FULL, acc, kap);
-            const int sigma = (kap - 1 - lane) & 31, j = k - 1 - sigma;
-            const double l = (j >= 0) ? sh.u.ring[(j >> 3) % RING_UNITS][(j & 7) * LTG + sigma] : 0.0;
-            if (lane == kap) {
-                x[k] = xk;
-                acc = fma(-l, xk, tk);                 // this lane moves on to row k - 32
-                tk = (k - 64 >= 0) ? F.TP[k - 64] : 0.0;
-            } else {
-                acc = fma(-l, xk, acc);
+        SEG(1);
+        const double *ltU = sh.u.ring[U % RING_UNITS];
+        const int r1 = k0 - 24 + lane, r2 = k0 - 32 + lane;
+        // rows of this lane: r1 in unit U - 3 + (lane >> 3), r2 (lanes 0..7) in unit U - 4, both at row lane & 7 of their unit
+        const double *p1 = &sh.u.ring[(U + 4 + (lane >> 3)) % RING_UNITS][(lane & 7) * FROW];
+        const double *p2 = &sh.u.ring[(U + 3) % RING_UNITS][(lane & 7) * FROW];
+        double l1[8], l2[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int o1 = 23 - lane + m, o2 = 31 - lane + m;          // k0 + m - row - 1
+            l1[m] = (r1 >= 0 && o1 >= 0) ? p1[o1] : 0.0;
+            l2[m] = (lane < 8 && r2 >= 0 && o2 <= 31) ? p2[o2] : 0.0;
+        }
+        double acc2 = (lane < 8 && r2 >= 0) ? p2[32] : 0.0;            // t of the entering row
+        double l11[28];                            // L[k0+mm][k0+m], mm > m: all loads before the chain
+#pragma unroll
+        for (int m = 0; m < 7; ++m)
+#pragma unroll
+            for (int mm = m + 1; mm < 8; ++mm) l11[(mm * (mm - 1)) / 2 + m] = ltU[m * FROW + (mm - m - 1)];
+        SEG(2);
+        double xv[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) xv[m] = __shfl_sync(FULL, acc, 24 + m);
+        SEG(3);
+#pragma unroll
+        for (int mm = 7; mm >= 1; --mm)            // right-looking: xv[mm] is final, the updates of one column are independent
+#pragma unroll
+            for (int m = 0; m < mm; ++m) xv[m] = fma(-l11[(mm * (mm - 1)) / 2 + m], xv[mm], xv[m]);
+        {
+            double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+#pragma unroll
+            for (int m = 0; m < 8; m += 2) {
+                e0 = fma(l1[m], xv[m], e0); e1 = fma(l1[m + 1], xv[m + 1], e1);
+                f0 = fma(l2[m], xv[m], f0); f1 = fma(l2[m + 1], xv[m + 1], f1);
             }
+            acc -= e0 + e1;                         // (lanes 24..31 end up with their own x)
+            acc2 -= f0 + f1;
+        }
+        SEG(4);
+        if (lane >= 24 && r1 < NA) x[r1] = acc;
+        {
+            const double dn = __shfl_sync(FULL, acc, (lane - 8) & 31);
+            acc = (lane >= 8) ? dn : acc2;
         }
         __syncwarp();
-        if (lane == 0 && U - 6 >= 0) R.issue(U - 6, F.LT + (size_t)(U - 6) * SUB * LTG, LT_UNIT_BYTES);   // slot of unit U + 1
+        SEG(5);
+        if (lane == 0 && U - 6 >= 0) R.issue(U - 6, LTp);            // slot of unit U + 1
+        SEG(6);
     }
+    SEG(20);
     R.close();
+    SEG(21);
 }
 
 // x = M^-1 g with the stored factor.  fused: the forward part was done inside factor() (predictor).
@@ -547,15 +789,23 @@ __device__ __noinline__ void solve(IpShared &sh, double *slab, const Layout &L, 
     fence_proxy_async();        // the ring area was last accessed through the generic proxy (factor hand-off buffers)
     __syncthreads();
     if (!fused) {
-        if (warp == 0) sweep_forward(sh, F, g);
+        PROF_T0(t0);
+        if (warp == 0) sweep_forward(sh, F.HB, F.LT, F.GT, F.NA, g);
         __syncthreads();
-        if (warp == 1) sweep_sep_rhs(sh, F, g);
+        PROF_ADD(2, t0);
+        PROF_T0(t1);
+        if (warp == 1) sweep_sep_rhs(sh, F.HB, F.LT, F.GT, F.NA, g);
         __syncwarp();
+        PROF_ADD1(3, t1);
     }
-    if (warp == 1) sweep_sep_solve(sh, F, x);
+    PROF_T0(t2);
+    if (warp == 1) sweep_sep_solve(sh, F.HB, F.LT, F.GT, F.NA, x);
+    PROF_ADD1(4, t2);
     __syncthreads();
-    if (warp == 0) sweep_backward(sh, F, x);
+    PROF_T0(t3);
+    if (warp == 0) sweep_backward(sh, F.HB, F.LT, F.GT, F.NA, x);
     __syncthreads();
+    PROF_ADD(8, t3);
 }
 
 // banded cyclic mat-vec out = H v (real-indexed)
@@ -580,7 +830,7 @@ __device__ void band_matvec(const double *__restrict__ HB, const double *__restr
 __device__ __forceinline__ void ip_init_shared(IpShared &sh) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < HB_SLOTS; ++i) mbar_init(&sh.hb_full[i], 1);
-        for (int i = 0; i < LT_SLOTS; ++i) { mbar_init(&sh.lt_full[i], 1); mbar_init(&sh.lt_empty[i], 1); }
+        for (int i = 0; i < HO_SLOTS; ++i) { mbar_init(&sh.ho_full[i], 1); mbar_init(&sh.ho_empty[i], 1); }
         for (int i = 0; i < RING_UNITS; ++i) mbar_init(&sh.ring_full[i], 1);
         sh.ring_phase = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -840,9 +1090,19 @@ size_t pdip_smem_bytes() { return sizeof(IpShared); }
 int debug_read_profile(unsigned long long *host_out, int reset) {
 #ifdef MC_PROFILE
     if (cudaMemcpyFromSymbol(host_out, g_prof, sizeof(unsigned long long) * 24) != cudaSuccess) return -1;
+    if (const char *e = getenv("MC_PROFILE_SEGMENTS")) {       // tools/prof_run.py: sub-phase counters of one panel
+        (void)e;
+        unsigned long long seg[32];
+        if (cudaMemcpyFromSymbol(seg, g_seg, sizeof(seg)) == cudaSuccess) {
+            fprintf(stderr, "segments:");
+            for (int i = 0; i < 32; ++i) fprintf(stderr, " %d:%llu", i, seg[i]);
+            fprintf(stderr, "\n");
+        }
+    }
     if (reset) {
-        unsigned long long z[24] = {0};
-        if (cudaMemcpyToSymbol(g_prof, z, sizeof(z)) != cudaSuccess) return -1;
+        unsigned long long z[32] = {0};
+        if (cudaMemcpyToSymbol(g_prof, z, sizeof(unsigned long long) * 24) != cudaSuccess) return -1;
+        cudaMemcpyToSymbol(g_seg, z, sizeof(z));
     }
     return 0;
 #else

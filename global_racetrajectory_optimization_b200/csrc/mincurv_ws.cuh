@@ -4,7 +4,7 @@
 //   [NUM_VEC][np]        O(N) vectors (geometry, linearisation, interior-point iterates)
 //   [n_max][ZB_PITCH]    bands of B_t = Ti diag(w_t) Ti, t = 0..2  (assembly scratch, mincurv_setup.cu)
 //   [np][HB_PITCH]       band of H = E^T E              (row i: H[i][i .. i+32], cyclic)
-//   [np][32] + [np][33]  bordered LDL^T factor of H + D: unit-lower columns L, fill columns G (mincurv_ipm.cu)
+//   2 x [np][34]         bordered LDL^T factor of H + D: unit-lower columns L, fill columns G (mincurv_ipm.cu)
 #pragma once
 #include "common.cuh"
 
@@ -19,7 +19,6 @@ enum Vec : int {
     V_ISU, V_ISL, V_YPAD,                                   // reciprocal slacks, padded forward-solve vector
     V_S3, V_S4, V_L3, V_L4, V_KL, V_WK, V_EDX, V_T3K, V_T4K, V_VV,   // curvature-row phase (K2b')
     V_IH,                                                   // 1 / h
-    V_WP, V_TP,                                             // 1 / d_k of the LDL^T factor, right-hand side of the backward sweep
     NUM_VEC
 };
 
@@ -42,7 +41,7 @@ __host__ __device__ inline Layout make_layout(int n_max) {
     L.o_hb = o;
     o += (size_t)L.np * HB_PITCH;
     L.o_tiles = o;
-    o += (size_t)L.np * (32 + 33);
+    o += (size_t)L.np * 68;
     L.stride = (o + 15) & ~(size_t)15;
     return L;
 }

@@ -120,7 +120,8 @@ def main():
     imp = {}
     for csv, opts in (("berlin_2018", dict(flip_imp_track=False, set_new_start=False, new_start=np.array([0.0, -47.0]), num_laps=1)),
                       ("handling_track", dict(flip_imp_track=True, set_new_start=True, new_start=np.array([0.0, -47.0]), num_laps=2)),
-                      ("rounded_rectangle", dict(flip_imp_track=False, set_new_start=True, new_start=np.array([10.0, 5.0]), num_laps=1))):
+                      ("rounded_rectangle", dict(flip_imp_track=False, set_new_start=True, new_start=np.array([10.0, 5.0]), num_laps=1)),
+                      ("modena_2019", dict(flip_imp_track=False, set_new_start=False, new_start=np.array([0.0, 0.0]), num_laps=1))):
         path = os.path.join(REF, "inputs", "tracks", csv + ".csv")
         buf = io.StringIO()
         with contextlib.redirect_stdout(buf):
