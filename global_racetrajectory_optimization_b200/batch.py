@@ -739,3 +739,34 @@ def check_normals_crossing_batch(track: torch.Tensor, normvec: torch.Tensor, hor
                                                  _stream())
         _lib.check(rc, "mc_check_normals_crossing_batch")
     return crossing != 0
+
+
+# ------------------------------------------------------------------------------------------------
+# sweep inputs generated on the device: width-jitter variants from seeds
+# ------------------------------------------------------------------------------------------------
+@_device_guard
+def jitter_widths_batch(base: torch.Tensor, seeds: torch.Tensor, rel: float = 0.1, centre_id: Optional[torch.Tensor] = None,
+                        n_pts_base: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+    """V = len(seeds) width-jitter variants of the prepared tracks ``base`` [n_base, n_max, 4] (variant v uses track
+    centre_id[v], default v % n_base): w <- w (1 + rel g(s)), g smooth with |g| <= 1 drawn from seeds[v] (int64) by the
+    stateless hash that synth.jitter_widths_hash mirrors on the host.  Returns (tracks [V, n_max, 4], n_pts [V])."""
+    _require_cuda()
+    lib = _lib.load()
+    base = _f64(base, "base")
+    n_base, n_max, four = base.shape
+    if four != 4:
+        raise ValueError("base must be [n_base, n_max, 4]")
+    dev = base.device
+    seeds = seeds.to(device=dev, dtype=torch.int64).contiguous()
+    V = int(seeds.numel())
+    if centre_id is not None:
+        centre_id = centre_id.to(device=dev, dtype=torch.int32).contiguous()
+        if centre_id.numel() != V:
+            raise ValueError("centre_id must have one entry per variant")
+    if out is None:
+        out = torch.empty((V, n_max, 4), dtype=torch.float64, device=dev)
+    n_out = torch.empty((V,), dtype=torch.int32, device=dev)
+    rc = lib.mc_jitter_widths_batch(V, n_max, _ptr(_npts(n_pts_base, n_base, dev)), n_base, _ptr(base), _ptr(centre_id),
+                                    _ptr(seeds), float(rel), _ptr(out), _ptr(n_out), _stream())
+    _lib.check(rc, "mc_jitter_widths_batch")
+    return out, n_out

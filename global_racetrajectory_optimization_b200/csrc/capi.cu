@@ -52,6 +52,8 @@ void launch_traj_extrema(int, int, const int32_t *, const double *, const double
 void launch_assemble_trajectory(int, int, const int32_t *, const double *, const double *, const double *, const double *,
                                 const double *, const double *, int, const int32_t *, const double *, double *, cudaStream_t);
 void launch_normals_crossing(int, int, const int32_t *, const double *, const double *, int, int32_t *, cudaStream_t);
+void launch_jitter_widths(int, int, const int32_t *, int, const double *, const int32_t *, const int64_t *, double, double *,
+                          int32_t *, cudaStream_t);
 }  // namespace mc
 
 static thread_local char g_err[256] = "";
@@ -458,6 +460,15 @@ int mc_check_normals_crossing_batch(int B, int n_max, const int32_t *n_pts, cons
         return bad("mc_check_normals_crossing_batch: bad argument");
     mc::launch_normals_crossing(B, n_max, n_pts, track, normvec, horizon, crossing, (cudaStream_t)stream);
     return check_cuda("normals_crossing_kernel");
+}
+
+int mc_jitter_widths_batch(int V, int n_max, const int32_t *n_pts_base, int n_base, const double *base,
+                           const int32_t *centre_id, const int64_t *seed, double rel, double *out, int32_t *n_pts_out,
+                           void *stream) {
+    if (V <= 0 || n_max <= 0 || n_base <= 0 || !base || !seed || !out || !(rel >= 0.0) || rel >= 1.0)
+        return bad("mc_jitter_widths_batch: bad argument");
+    mc::launch_jitter_widths(V, n_max, n_pts_base, n_base, base, centre_id, seed, rel, out, n_pts_out, (cudaStream_t)stream);
+    return check_cuda("jitter_widths_kernel");
 }
 
 /* debug aid (tests/test_gpu_factor.py): one factorisation + the two kinds of solve of the interior-point kernel on slabs

@@ -87,3 +87,35 @@ def discrete_curvature(xy: np.ndarray) -> np.ndarray:
     c = np.linalg.norm(p2 - p0, axis=1)
     cross = (p1[:, 0] - p0[:, 0]) * (p2[:, 1] - p0[:, 1]) - (p1[:, 1] - p0[:, 1]) * (p2[:, 0] - p0[:, 0])
     return 2.0 * cross / (a * b * c)
+
+
+# ----------------------------------------------------------------------------------------------
+# host mirror of csrc/synth.cu (variants generated on the device from a 64-bit seed per variant)
+# ----------------------------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+
+
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+def _u01(h: int) -> float:
+    return (h >> 11) * (1.0 / 9007199254740992.0)
+
+
+def jitter_widths_hash(reftrack: np.ndarray, seed: int, rel: float = 0.1) -> np.ndarray:
+    """The variant mc_jitter_widths_batch generates on the device for this seed (identical up to the last ulp of cos)."""
+    n = reftrack.shape[0]
+    u = np.arange(n) / n
+    out = reftrack.copy()
+    for s in range(2):
+        g = np.zeros(n)
+        for k in range(3):
+            h0 = _splitmix64((seed * 6 + 2 * (3 * s + k)) & _M64)
+            h1 = _splitmix64((seed * 6 + 2 * (3 * s + k) + 1 + 0x5851F42D4C957F2D) & _M64)
+            g += (2.0 * _u01(h0) - 1.0) * np.cos(2.0 * np.pi * (k + 1) * u + 2.0 * np.pi * _u01(h1))
+        out[:, 2 + s] = reftrack[:, 2 + s] * (1.0 + rel * (g * (1.0 / 3.0)))
+    return out

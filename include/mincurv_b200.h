@@ -282,6 +282,18 @@ int mc_assemble_trajectory_batch(int B, int n_max, const int32_t *n_traj, const 
 int mc_check_normals_crossing_batch(int B, int n_max, const int32_t *n_pts, const double *track, const double *normvec,
                                     int horizon, int32_t *crossing, void *stream);
 
+/* -------------------------------------------------------------------------------------------------
+ * Sweep inputs generated on the device (no counterpart in tph: the reference builds its parameter sweeps in Python
+ * loops around one prepared track, /root/reference/main_globaltraj.py:442-496): V width-jitter variants of n_base
+ * prepared tracks, w <- w (1 + rel g(s)) with a smooth g, |g| <= 1, drawn from the 64-bit seed of the variant by a
+ * stateless hash (splitmix64) that global_racetrajectory_optimization_b200/synth.py mirrors in numpy.
+ *   base [n_base][n_max][4], n_pts_base [n_base] or NULL, centre_id [V] (int32) or NULL => variant v uses track v % n_base,
+ *   seed [V] (int64), out [V][n_max][4], n_pts_out [V] or NULL
+ */
+int mc_jitter_widths_batch(int V, int n_max, const int32_t *n_pts_base, int n_base, const double *base,
+                           const int32_t *centre_id, const int64_t *seed, double rel, double *out, int32_t *n_pts_out,
+                           void *stream);
+
 /* Debug aid (synchronous): reads (and optionally clears) 24 cycle counters that CTA 0 of mincurv_pdip_kernel
  * accumulates per phase -- used by tools/prof_run.py to attribute time inside the kernel. Host pointer. */
 int mc_debug_read_profile(unsigned long long *host_out24, int reset);

@@ -173,3 +173,22 @@ def test_c5_shortest_path_interleaved_with_mincurv_on_two_streams(golden):
     for sp, mc in outs:
         assert torch.equal(sp["alpha"], sp0["alpha"]) and torch.equal(sp["status"], sp0["status"])
         assert torch.equal(mc["alpha"], mc0["alpha"]) and torch.equal(mc["status"], mc0["status"])
+
+
+def test_device_generated_variants_match_the_host_mirror():
+    """mc_jitter_widths_batch (inputs of the C2 / C4 sweeps generated on the device from one 64-bit seed per variant)
+    against synth.jitter_widths_hash, the numpy statement of the same stateless hash."""
+    dev = torch.device("cuda")
+    base = synth.make_batch(300, 3, 257)
+    seeds = np.array([0, 1, 2, 12345678901, 2 ** 40 + 7, 99], dtype=np.int64)
+    cid = np.array([0, 1, 2, 0, 1, 2], dtype=np.int32)
+    out, n_out = B_.jitter_widths_batch(torch.tensor(base, device=dev), torch.tensor(seeds), rel=0.1, centre_id=torch.tensor(cid))
+    out = out.cpu().numpy()
+    assert n_out.cpu().tolist() == [257] * 6
+    for v in range(6):
+        ref = synth.jitter_widths_hash(base[cid[v]], int(seeds[v]), 0.1)
+        assert np.array_equal(out[v, :, :2], ref[:, :2]) and np.abs(out[v, :, 2:] - ref[:, 2:]).max() <= 1e-12
+    assert np.abs(out[0, :, 2] / base[0, :, 2] - 1.0).max() <= 0.1 + 1e-12 and np.abs(out[0, :, 2] - out[3, :, 2]).max() > 1e-3
+    # default centre assignment: variant v uses track v % n_base
+    out2, _ = B_.jitter_widths_batch(torch.tensor(base, device=dev), torch.tensor(seeds[:3]))
+    assert np.array_equal(out2.cpu().numpy(), out[:3])

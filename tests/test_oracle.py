@@ -164,3 +164,21 @@ def test_iqp_history_matches_golden(golden):
     assert rel_max(a, g["iqp_alpha"]) < 1e-6
     assert rt_new.shape == g["iqp_reftrack"].shape and np.abs(rt_new - g["iqp_reftrack"]).max() < 1e-6
     assert np.all(rt[:, 2:] == g["reftrack"][:, 2:])       # the oracle does not mutate the caller's widths
+
+
+# ---- the banded CPU port of the path (oracle/banded_cpu.c: bench.py's fair CPU baseline) against the dense oracle ----
+@pytest.mark.parametrize("name", ["berlin", "handling", "synth200", "synth500", "synth1000"])
+def test_banded_cpu_port_matches_the_dense_oracle(golden, name):
+    from oracle import banded_cpu as BC
+    g = golden(name)
+    alpha, iters = BC.opt_min_curv_banded(g["reftrack"], g["normvec"], float(g["w_veh"]), f_scale=T.F_SCALE)
+    ref = g["alpha_mincurv_boxonly"]              # box-only QP: the dense oracle's Goldfarb-Idnani solve without curvature rows
+    assert 5 <= iters <= 30
+    assert np.abs(alpha - ref).max() <= 1e-7 * np.abs(ref).max()
+
+
+def test_banded_cpu_port_reports_a_track_that_is_too_narrow(golden):
+    from oracle import banded_cpu as BC
+    g = golden("synth200")
+    with pytest.raises(RuntimeError, match="Problem not solvable"):
+        BC.opt_min_curv_banded(g["reftrack"], g["normvec"], 20.0)
