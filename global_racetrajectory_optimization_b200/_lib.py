@@ -39,6 +39,7 @@ _SIGS = {
     "mc_iqp_relinearise_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_dbl, _c_int, _vp, _vp, _vp, _vp,
                                           _sz, _vp]),
     "mc_scale_alpha_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _c_dbl, _vp]),
+    "mc_iqp_finish_batch": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int] + [_vp] * 16),
     "mc_vel_profile_workspace_bytes": (_sz, [_c_int, _c_int, _c_int]),
     "mc_vel_profile_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _c_dbl, _c_int, _vp, _c_int, _vp,
                                       _c_dbl, _c_dbl, _c_dbl, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -53,6 +54,7 @@ _SIGS = {
     "mc_traj_extrema_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_dbl, _c_dbl, _vp, _vp]),
     "mc_assemble_trajectory_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp]),
     "mc_check_normals_crossing_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp]),
+    "mc_polygon_length_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _c_int, _vp, _vp, _c_int, _c_dbl, _vp, _vp]),
     "mc_jitter_widths_batch": (_c_int, [_c_int, _c_int, _vp, _c_int, _vp, _vp, _vp, _c_dbl, _vp, _vp, _vp]),
     "mc_debug_read_profile": (_c_int, [_vp, _c_int]),
     "mc_debug_factor_solve": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _sz, _vp]),

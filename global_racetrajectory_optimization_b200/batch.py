@@ -228,17 +228,17 @@ def opt_shortest_path_batch(reftrack: torch.Tensor, normvec: torch.Tensor, w_veh
     return dict(alpha=alpha, status=status, iters=iters)
 
 
-def _closed_polygon_length(pts: torch.Tensor, n_pts: Optional[torch.Tensor]) -> torch.Tensor:
-    """Length [B] of the closed polygon through the first n_pts[b] points of every row (padding ignored)."""
-    B, n_max, _ = pts.shape
-    seg = (torch.roll(pts, -1, dims=1) - pts).norm(dim=-1)
-    if n_pts is None:
-        return seg.sum(dim=1)
-    idx = torch.arange(n_max, device=pts.device).unsqueeze(0)
-    last = (n_pts.long() - 1).clamp(min=0).unsqueeze(1)
-    closing = (pts[:, 0, :] - torch.gather(pts, 1, last.unsqueeze(-1).expand(-1, 1, 2)).squeeze(1)).norm(dim=-1)
-    seg = torch.where(idx < last, seg, torch.zeros_like(seg))
-    return seg.sum(dim=1) + closing
+def _closed_polygon_length(pts: torch.Tensor, n_pts: Optional[torch.Tensor], normvec: Optional[torch.Tensor] = None,
+                           shift: Optional[torch.Tensor] = None, shift_stride: int = 1, sign: float = 1.0) -> torch.Tensor:
+    """Length [B] of the closed polygon through the first n_pts[b] points p_i (+ sign * shift_i * n_i) of every row
+    (mc_polygon_length_batch: a block reduction per track on the device)."""
+    lib = _lib.load()
+    B, n_max, stride = pts.shape
+    out = torch.zeros((B,), dtype=torch.float64, device=pts.device)
+    rc = lib.mc_polygon_length_batch(B, n_max, _ptr(n_pts), _ptr(pts), stride, _ptr(normvec), _ptr(shift), int(shift_stride),
+                                     float(sign), _ptr(out), _stream())
+    _lib.check(rc, "mc_polygon_length_batch")
+    return out
 
 
 @_device_guard
@@ -260,7 +260,7 @@ def create_raceline_batch(refline: torch.Tensor, normvec: torch.Tensor, alpha: t
     n_pts = _npts(n_pts, B, dev)
     derived = n_out_max is None
     if derived:
-        poly = _closed_polygon_length(refline[:, :, :2] + alpha.unsqueeze(-1) * normvec, n_pts)
+        poly = _closed_polygon_length(refline, n_pts, normvec=normvec, shift=alpha)
         n_out_max = int(math.ceil(float(poly.max().item()) * 1.1 / float(stepsize_interp))) + 16
     n_out_max = int(n_out_max)
     while True:
@@ -367,6 +367,8 @@ def iqp_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, ka
     re-linearisation; an instance leaves the loop once iter >= iters_min and its curv_error_max <=
     curv_error_allowed.  Returns dict(alpha [B, n_cap], reftrack [B, n_cap, 4], normvec [B, n_cap, 2],
     n_pts [B], outer_iters [B], status [B], qp_solves) -- every array refers to the instance's LAST iteration.
+    status: the QP status of that iteration, or 2 if max_iters outer iterations did not reach curv_error_allowed (tph
+    would keep iterating).  One small device->host read per outer iteration.
 
     fixed_iters: run exactly that many outer iterations for every instance (bench config C3)."""
     _require_cuda()
@@ -380,7 +382,7 @@ def iqp_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, ka
     # capacity of the re-sampled tracks: the raceline is re-sampled every stepsize_interp metres, so its point count
     # follows from its length, not from n_max (a track given at a coarser spacing grows); 5 % + 50 m of slack on the
     # reference polygon, and the relinearisation step below grows the buffers if a track still does not fit
-    poly = float(_closed_polygon_length(reftrack[:, :, :2], cur_n).max().item())
+    poly = float(_closed_polygon_length(reftrack, cur_n).max().item())
     n_cap = max(n_max + 64, int(math.ceil((1.05 * poly + 50.0) / float(stepsize_interp))) + 16)
 
     def _alloc(cap):
@@ -388,51 +390,51 @@ def iqp_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, ka
                     reftrack=torch.zeros((B, cap, 4), dtype=torch.float64, device=dev),
                     normvec=torch.zeros((B, cap, 2), dtype=torch.float64, device=dev))
 
+    lib = _lib.load()
     fin = _alloc(n_cap)
     fin.update(n_pts=torch.zeros((B,), dtype=torch.int32, device=dev),
                outer_iters=torch.zeros((B,), dtype=torch.int32, device=dev),
                status=torch.zeros((B,), dtype=torch.int32, device=dev),
                curv_error_max=torch.zeros((B,), dtype=torch.float64, device=dev))
-    active = torch.ones((B,), dtype=torch.bool, device=dev)
+    active = torch.ones((B,), dtype=torch.int32, device=dev)
+    counters = torch.zeros((2,), dtype=torch.int32, device=dev)
+    n_active = B
     qp_solves = 0
     it = 0
     limit = fixed_iters if fixed_iters is not None else max_iters
     while True:
         it += 1
         n_cur_max = reftrack.shape[1]
-        res = opt_min_curv_batch(reftrack, normvec, h, kappa_bound, w_veh, n_pts=cur_n)
-        qp_solves += int(active.sum().item())
+        res = opt_min_curv_batch(reftrack, normvec, h, kappa_bound, w_veh, n_pts=cur_n)     # (finished tracks: n_pts = 0, skipped)
+        qp_solves += n_active
         alpha = res["alpha"]
         if it < iters_min:
             scale_alpha_batch(alpha, it * 1.0 / iters_min)
-        failed = res["status"] != 0
-        if fixed_iters is not None:
-            done = active & (torch.full_like(active, it >= fixed_iters) | failed)
-        else:
-            done = active & (((res["curv_error_max"] <= curv_error_allowed) & (it >= iters_min)) | failed | (it >= limit))
-        if bool(done.any().item()):
-            idx = done.nonzero(as_tuple=True)[0]
-            fin["alpha"][idx, :n_cur_max] = alpha[idx]
-            fin["reftrack"][idx, :n_cur_max] = reftrack[idx]
-            fin["normvec"][idx, :n_cur_max] = normvec[idx]
-            fin["n_pts"][idx] = cur_n[idx]
-            fin["outer_iters"][idx] = it
-            fin["status"][idx] = res["status"][idx]
-            fin["curv_error_max"][idx] = res["curv_error_max"][idx]
-        active = active & ~done
-        if not bool(active.any().item()):
+        # per-track termination and the copy of finished tracks into the result buffers: on the device
+        rc = lib.mc_iqp_finish_batch(B, n_cur_max, n_cap, it, int(iters_min), float(curv_error_allowed),
+                                     int(fixed_iters) if fixed_iters is not None else 0, int(limit), _ptr(active),
+                                     _ptr(res["status"]), _ptr(res["curv_error_max"]), _ptr(cur_n), _ptr(alpha), _ptr(reftrack),
+                                     _ptr(normvec), _ptr(fin["alpha"]), _ptr(fin["reftrack"]), _ptr(fin["normvec"]),
+                                     _ptr(fin["n_pts"]), _ptr(fin["outer_iters"]), _ptr(fin["status"]),
+                                     _ptr(fin["curv_error_max"]), _ptr(counters), _stream())
+        _lib.check(rc, "mc_iqp_finish_batch")
+        if it >= limit:                       # every track was finished by this call (fixed count or cap): nothing to read back
             break
         while True:
             rt_new, nv_new, n_new = iqp_relinearise_batch(reftrack, normvec, alpha, stepsize_interp, n_pts=cur_n,
                                                           active=active, n_max_new=n_cap)
-            too_big = active & (n_new < 0)
-            if not bool(too_big.any().item()):
+            # the ONE host read of the iteration: tracks still active, and the smallest new point count (negative = -(points
+            # needed) for a track that does not fit the capacity)
+            n_active, n_min = (int(v) for v in torch.stack((counters[0], n_new.min())).tolist())
+            if n_active == 0 or n_min >= 0:
                 break
-            n_cap = int((-n_new[too_big]).max().item()) + 64        # the kernel reports -(required size)
+            n_cap = -n_min + 64
             grown = _alloc(n_cap)
             for k in ("alpha", "reftrack", "normvec"):
                 grown[k][:, :fin[k].shape[1]] = fin[k]
                 fin[k] = grown[k]
+        if n_active == 0:
+            break
         reftrack, normvec, cur_n = rt_new, nv_new, n_new
         h = torch.ones((B, n_cap), dtype=torch.float64, device=dev)   # use_dist_scaling=False from iteration 2 on
     fin["qp_solves"] = qp_solves
@@ -591,9 +593,12 @@ def interp_track_batch(pts: torch.Tensor, stepsize_approx: float = 1.0, n_pts: O
         if normvec.shape != (B, n_max, 2) or stride != 4:
             raise ValueError("normvec needs a [B, n_max, 4] track and must be [B, n_max, 2]")
     if n_out_max is None:
-        line = pts[:, :, :2] if normvec is None else \
-            pts[:, :, :2] + float(normal_sign) * normvec * pts[:, :, int(width_col)].unsqueeze(-1)
-        n_out_max = int(math.ceil(float(_closed_polygon_length(line, n_pts).max().item()) / float(stepsize_approx))) + 8
+        if normvec is None:
+            poly = _closed_polygon_length(pts, n_pts)
+        else:       # the boundary polyline p + sign * w n: the width column of the track is the per-point shift (stride 4)
+            poly = _closed_polygon_length(pts, n_pts, normvec=normvec, shift=pts.reshape(-1)[int(width_col):].view(-1),
+                                          shift_stride=4, sign=float(normal_sign))
+        n_out_max = int(math.ceil(float(poly.max().item()) / float(stepsize_approx))) + 8
     ws = _workspace("interp_track", lib.mc_interp_track_workspace_bytes(B, n_max), dev)
     while True:
         out = torch.zeros((B, int(n_out_max), 4), dtype=torch.float64, device=dev)

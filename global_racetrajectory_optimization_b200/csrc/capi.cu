@@ -33,6 +33,9 @@ void launch_iqp_new_reftrack(int, int, const int32_t *, const int32_t *, const d
                              int, const int32_t *, const double *, const int32_t *, const double *, double *, double *,
                              int32_t *, cudaStream_t);
 void launch_scale_alpha(int, int, double *, const double *, double, cudaStream_t);
+void launch_iqp_finish(int, int, int, int, int, double, int, int, int32_t *, const int32_t *, const double *, const int32_t *,
+                       const double *, const double *, const double *, double *, double *, double *, int32_t *, int32_t *,
+                       int32_t *, double *, int32_t *, cudaStream_t);
 size_t shortest_path_ws_doubles(int n_max);
 int launch_shortest_path(int, int, const int32_t *, const double *, const double *, double, const double *, double *,
                          int32_t *, int32_t *, double *, cudaStream_t);
@@ -52,6 +55,8 @@ void launch_traj_extrema(int, int, const int32_t *, const double *, const double
 void launch_assemble_trajectory(int, int, const int32_t *, const double *, const double *, const double *, const double *,
                                 const double *, const double *, int, const int32_t *, const double *, double *, cudaStream_t);
 void launch_normals_crossing(int, int, const int32_t *, const double *, const double *, int, int32_t *, cudaStream_t);
+void launch_polygon_length(int, int, const int32_t *, const double *, int, const double *, const double *, int, double, double *,
+                           cudaStream_t);
 void launch_jitter_widths(int, int, const int32_t *, int, const double *, const int32_t *, const int64_t *, double, double *,
                           int32_t *, cudaStream_t);
 }  // namespace mc
@@ -462,6 +467,15 @@ int mc_check_normals_crossing_batch(int B, int n_max, const int32_t *n_pts, cons
     return check_cuda("normals_crossing_kernel");
 }
 
+int mc_polygon_length_batch(int B, int n_max, const int32_t *n_pts, const double *pts, int stride, const double *normvec,
+                            const double *shift, int shift_stride, double sign, double *length, void *stream) {
+    if (B <= 0 || n_max <= 0 || !pts || stride < 2 || !length || ((normvec == nullptr) != (shift == nullptr)) ||
+        (shift && shift_stride < 1))
+        return bad("mc_polygon_length_batch: bad argument");
+    mc::launch_polygon_length(B, n_max, n_pts, pts, stride, normvec, shift, shift_stride, sign, length, (cudaStream_t)stream);
+    return check_cuda("polygon_length_kernel");
+}
+
 int mc_jitter_widths_batch(int V, int n_max, const int32_t *n_pts_base, int n_base, const double *base,
                            const int32_t *centre_id, const int64_t *seed, double rel, double *out, int32_t *n_pts_out,
                            void *stream) {
@@ -485,6 +499,22 @@ int mc_debug_factor_solve(int B, int n_max, const int32_t *n_pts, int32_t *statu
 
 int mc_debug_read_profile(unsigned long long *host_out16, int reset) {
     return mc::debug_read_profile(host_out16, reset) == 0 ? MC_OK : MC_ECUDA;
+}
+
+int mc_iqp_finish_batch(int B, int n_max, int n_cap, int iter, int iters_min, double curv_error_allowed, int fixed_iters,
+                        int iter_limit, int32_t *active, const int32_t *status, const double *curv_error_max,
+                        const int32_t *n_pts, const double *alpha, const double *reftrack, const double *normvec,
+                        double *fin_alpha, double *fin_reftrack, double *fin_normvec, int32_t *fin_n_pts,
+                        int32_t *fin_outer_iters, int32_t *fin_status, double *fin_curv_error_max, int32_t *counters,
+                        void *stream) {
+    if (B <= 0 || n_max <= 0 || n_cap < n_max || iter < 1 || !active || !status || !curv_error_max || !alpha || !reftrack ||
+        !normvec || !fin_alpha || !fin_reftrack || !fin_normvec || !fin_n_pts || !fin_outer_iters || !fin_status ||
+        !fin_curv_error_max || !counters)
+        return bad("mc_iqp_finish_batch: bad argument");
+    mc::launch_iqp_finish(B, n_max, n_cap, iter, iters_min, curv_error_allowed, fixed_iters, iter_limit, active, status,
+                          curv_error_max, n_pts, alpha, reftrack, normvec, fin_alpha, fin_reftrack, fin_normvec, fin_n_pts,
+                          fin_outer_iters, fin_status, fin_curv_error_max, counters, (cudaStream_t)stream);
+    return check_cuda("iqp_finish_kernel");
 }
 
 int mc_scale_alpha_batch(int B, int n_max, double *alpha, const double *scale_batch, double scale, void *stream) {

@@ -299,8 +299,13 @@ void launch_create_raceline(int B, int n_max, const int32_t *n_pts, const double
 void launch_head_curv(int B, int n_max, const double *cx, const double *cy, int n_eval_max, const int32_t *n_eval,
                       const int32_t *ind, const double *t, double *psi, double *kappa, double *dkappa,
                       cudaStream_t stream) {
-    dim3 grid((n_eval_max + 255) / 256, B);
-    head_curv_kernel<<<grid, 256, 0, stream>>>(n_max, cx, cy, n_eval_max, n_eval, ind, t, psi, kappa, dkappa);
+    for (int b0 = 0; b0 < B; b0 += 65535) {         // the track index is gridDim.y (<= 65535 per launch)
+        const int nb = (B - b0 < 65535) ? B - b0 : 65535;
+        const size_t oe = (size_t)b0 * n_eval_max, oc = (size_t)b0 * n_max * 4;
+        dim3 grid((n_eval_max + 255) / 256, nb);
+        head_curv_kernel<<<grid, 256, 0, stream>>>(n_max, cx + oc, cy + oc, n_eval_max, n_eval ? n_eval + b0 : nullptr, ind + oe,
+                                                   t + oe, psi + oe, kappa ? kappa + oe : nullptr, dkappa ? dkappa + oe : nullptr);
+    }
 }
 void launch_iqp_new_reftrack(int B, int n_max, const int32_t *n_pts, const int32_t *active, const double *reftrack,
                              const double *normvec, const double *alpha, int n_max_new, const int32_t *n_new,
@@ -309,9 +314,66 @@ void launch_iqp_new_reftrack(int B, int n_max, const int32_t *n_pts, const int32
     iqp_new_reftrack_kernel<<<B, 256, 0, stream>>>(n_max, n_pts, active, reftrack, normvec, alpha, n_max_new, n_new,
                                                    race_xy, inds, tvals, reftrack_new, normvec_new, n_pts_new);
 }
+// ---------------------------------------------------------------------------------------------
+// tph.iqp_handler's per-track termination on the device: a track leaves the loop once
+// iter >= iters_min and curv_error_max <= curv_error_allowed (or its QP failed, or the iteration cap is reached: status 2);
+// its alpha / reftrack / normvectors of THIS iteration are copied into the result buffers and its `active` word is
+// cleared, so the host loop needs one small read per outer iteration (counters) instead of masks and gathers.
+__global__ void __launch_bounds__(256)
+iqp_finish_kernel(int n_max, int n_cap, int it, int iters_min, double curv_error_allowed, int fixed_iters, int limit,
+                  int32_t *__restrict__ active, const int32_t *__restrict__ status, const double *__restrict__ curv_err,
+                  const int32_t *__restrict__ n_pts, const double *__restrict__ alpha, const double *__restrict__ reftrack,
+                  const double *__restrict__ normvec, double *__restrict__ fin_alpha, double *__restrict__ fin_reftrack,
+                  double *__restrict__ fin_normvec, int32_t *__restrict__ fin_n_pts, int32_t *__restrict__ fin_iters,
+                  int32_t *__restrict__ fin_status, double *__restrict__ fin_curv_err, int32_t *__restrict__ counters) {
+    const int b = blockIdx.x;
+    if (!active[b]) return;
+    const int st = status[b];
+    const bool failed = st != 0;
+    bool done, capped = false;
+    if (fixed_iters > 0) done = (it >= fixed_iters) || failed;
+    else {
+        const bool conv = (curv_err[b] <= curv_error_allowed) && (it >= iters_min);
+        capped = !conv && !failed && it >= limit;
+        done = conv || failed || capped;
+    }
+    if (!done) {
+        if (threadIdx.x == 0) atomicAdd(&counters[0], 1);      // still active after this iteration
+        return;
+    }
+    const int n = n_pts ? n_pts[b] : n_max;
+    for (int i = threadIdx.x; i < n_cap; i += blockDim.x) {
+        const bool in = i < n && i < n_max;
+        fin_alpha[(size_t)b * n_cap + i] = in ? alpha[(size_t)b * n_max + i] : 0.0;
+        for (int c = 0; c < 4; ++c) fin_reftrack[((size_t)b * n_cap + i) * 4 + c] = in ? reftrack[((size_t)b * n_max + i) * 4 + c] : 0.0;
+        for (int c = 0; c < 2; ++c) fin_normvec[((size_t)b * n_cap + i) * 2 + c] = in ? normvec[((size_t)b * n_max + i) * 2 + c] : 0.0;
+    }
+    if (threadIdx.x == 0) {
+        fin_n_pts[b] = n;
+        fin_iters[b] = it;
+        fin_status[b] = capped ? 2 : st;          // 2: the outer-iteration cap was reached before curv_error_allowed
+        fin_curv_err[b] = curv_err[b];
+        active[b] = 0;
+        atomicAdd(&counters[1], 1);
+    }
+}
+void launch_iqp_finish(int B, int n_max, int n_cap, int it, int iters_min, double curv_error_allowed, int fixed_iters, int limit,
+                       int32_t *active, const int32_t *status, const double *curv_err, const int32_t *n_pts, const double *alpha,
+                       const double *reftrack, const double *normvec, double *fin_alpha, double *fin_reftrack,
+                       double *fin_normvec, int32_t *fin_n_pts, int32_t *fin_iters, int32_t *fin_status, double *fin_curv_err,
+                       int32_t *counters, cudaStream_t stream) {
+    cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), stream);
+    iqp_finish_kernel<<<B, 256, 0, stream>>>(n_max, n_cap, it, iters_min, curv_error_allowed, fixed_iters, limit, active, status,
+                                             curv_err, n_pts, alpha, reftrack, normvec, fin_alpha, fin_reftrack, fin_normvec,
+                                             fin_n_pts, fin_iters, fin_status, fin_curv_err, counters);
+}
+
 void launch_scale_alpha(int B, int n_max, double *alpha, const double *scale_batch, double scale, cudaStream_t stream) {
-    dim3 grid((n_max + 255) / 256, B);
-    scale_alpha_kernel<<<grid, 256, 0, stream>>>(n_max, alpha, scale_batch, scale);
+    for (int b0 = 0; b0 < B; b0 += 65535) {         // the track index is gridDim.y (<= 65535 per launch)
+        const int nb = (B - b0 < 65535) ? B - b0 : 65535;
+        dim3 grid((n_max + 255) / 256, nb);
+        scale_alpha_kernel<<<grid, 256, 0, stream>>>(n_max, alpha + (size_t)b0 * n_max, scale_batch ? scale_batch + b0 : nullptr, scale);
+    }
 }
 
 }  // namespace mc

@@ -62,6 +62,38 @@ jitter_widths_kernel(int V, int n_max, const int32_t *__restrict__ n_pts_base, i
     }
 }
 
+// Length of the closed polygon through the points p_i + s_i n_i of every track (s: a per-point shift such as alpha, or a
+// width column of the track times +-1; no normals: the points themselves) -- the host sizes re-sampling buffers from it
+// (create_raceline / interp_track / iqp_handler capacities) with one small read instead of torch reductions.
+__global__ void __launch_bounds__(256)
+polygon_length_kernel(int n_max, const int32_t *__restrict__ n_pts, const double *__restrict__ pts, int stride,
+                      const double *__restrict__ normvec, const double *__restrict__ shift, int shift_stride, double sign,
+                      double *__restrict__ length) {
+    const int b = blockIdx.x;
+    const int n = n_pts ? n_pts[b] : n_max;
+    __shared__ double red[32];
+    double acc = 0.0;
+    const double *P = pts + (size_t)b * n_max * stride;
+    const double *Nv = normvec ? normvec + (size_t)b * n_max * 2 : nullptr;
+    const double *S = shift ? shift + (size_t)b * n_max * shift_stride : nullptr;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int j = (i + 1 == n) ? 0 : i + 1;
+        double x0 = P[(size_t)i * stride], y0 = P[(size_t)i * stride + 1], x1 = P[(size_t)j * stride], y1 = P[(size_t)j * stride + 1];
+        if (Nv && S) {
+            const double s0 = sign * S[(size_t)i * shift_stride], s1 = sign * S[(size_t)j * shift_stride];
+            x0 += s0 * Nv[2 * i]; y0 += s0 * Nv[2 * i + 1]; x1 += s1 * Nv[2 * j]; y1 += s1 * Nv[2 * j + 1];
+        }
+        acc += sqrt((x1 - x0) * (x1 - x0) + (y1 - y0) * (y1 - y0));
+    }
+    acc = block_reduce<0>(acc, red);
+    if (threadIdx.x == 0) length[b] = (n > 1) ? acc : 0.0;
+}
+
+void launch_polygon_length(int B, int n_max, const int32_t *n_pts, const double *pts, int stride, const double *normvec,
+                           const double *shift, int shift_stride, double sign, double *length, cudaStream_t stream) {
+    polygon_length_kernel<<<B, 256, 0, stream>>>(n_max, n_pts, pts, stride, normvec, shift, shift_stride, sign, length);
+}
+
 void launch_jitter_widths(int V, int n_max, const int32_t *n_pts_base, int n_base, const double *base,
                           const int32_t *centre_id, const int64_t *seed, double rel, double *out, int32_t *n_pts_out,
                           cudaStream_t stream) {

@@ -294,6 +294,25 @@ int mc_jitter_widths_batch(int V, int n_max, const int32_t *n_pts_base, int n_ba
                            const int32_t *centre_id, const int64_t *seed, double rel, double *out, int32_t *n_pts_out,
                            void *stream);
 
+/* Length [B] of the closed polygon through the first n_pts[b] points of every track; with normvec and shift the points are
+ * p_i + sign * shift_i * n_i (shift: alpha [B][n_max] with shift_stride 1, or a width column &track[0][0][2] with
+ * shift_stride 4).  Used by the host to size the re-sampling buffers of create_raceline / interp_track / iqp_handler. */
+int mc_polygon_length_batch(int B, int n_max, const int32_t *n_pts, const double *pts, int stride, const double *normvec,
+                            const double *shift, int shift_stride, double sign, double *length, void *stream);
+
+/* tph.iqp_handler's per-track termination test (call site /root/reference/main_globaltraj.py:273-284) for
+ * outer iteration `iter` (1-based): an active track is finished when iter >= iters_min and curv_error_max <=
+ * curv_error_allowed, when its QP failed (status != 0), or when iter >= iter_limit (then fin_status = 2: cap reached before
+ * the tolerance).  fixed_iters > 0 replaces the test by iter >= fixed_iters.  Finished tracks get their alpha / reftrack /
+ * normvec rows of this iteration copied into the fin_* buffers (row pitch n_cap >= n_max) and active[b] = 0.
+ * counters [2] (int32, device): [0] tracks still active afterwards, [1] tracks finished by this call. */
+int mc_iqp_finish_batch(int B, int n_max, int n_cap, int iter, int iters_min, double curv_error_allowed, int fixed_iters,
+                        int iter_limit, int32_t *active, const int32_t *status, const double *curv_error_max,
+                        const int32_t *n_pts, const double *alpha, const double *reftrack, const double *normvec,
+                        double *fin_alpha, double *fin_reftrack, double *fin_normvec, int32_t *fin_n_pts,
+                        int32_t *fin_outer_iters, int32_t *fin_status, double *fin_curv_error_max, int32_t *counters,
+                        void *stream);
+
 /* Debug aid (synchronous): reads (and optionally clears) 24 cycle counters that CTA 0 of mincurv_pdip_kernel
  * accumulates per phase -- used by tools/prof_run.py to attribute time inside the kernel. Host pointer. */
 int mc_debug_read_profile(unsigned long long *host_out24, int reset);

@@ -87,7 +87,7 @@ def test_every_wrapper_matches_the_signature_table(fake):
     assert used >= set(_lib.EXPORTED_SYMBOLS) - {"mc_version", "mc_last_error", "mc_debug_read_profile", "mc_debug_factor_solve",
                                                  "mc_mincurv_setup_batch", "mc_mincurv_setup_batch_ex", "mc_mincurv_solve_batch",
                                                  "mc_vel_profile_batch", "mc_mincurv_pdip_batch", "mc_mincurv_finalize_batch",
-                                                 "mc_mincurv_kappa_batch"}
+                                                 "mc_mincurv_kappa_batch", "mc_iqp_finish_batch", "mc_jitter_widths_batch"}
 
 
 def test_launches_with_the_track_index_on_grid_y_are_chunked(fake, monkeypatch):
@@ -140,6 +140,22 @@ def test_iqp_batch_grows_its_buffers_when_a_resampled_track_does_not_fit(fake, m
                 ctypes.memset(a[13].value, 0, bq * 4)                            # status = 0
                 return 0
             return solve
+        if name == "mc_iqp_finish_batch":
+            def finish(*a):        # stand-in of the device-side termination test: curv_error_max = 0, so done once iter >= iters_min
+                fn(*a)
+                bq, it, iters_min = a[0], a[3], a[4]
+                done = it >= iters_min
+                i32 = lambda ptr, k: (ctypes.c_int32 * k).from_address(ptr.value)
+                counters, active = i32(a[22], 2), i32(a[8], bq)
+                counters[0], counters[1] = (0, bq) if done else (bq, 0)
+                if done:
+                    npts = i32(a[11], bq)
+                    for b in range(bq):
+                        active[b] = 0
+                        i32(a[18], bq)[b] = npts[b]          # fin_n_pts
+                        i32(a[19], bq)[b] = it               # fin_outer_iters
+                return 0
+            return finish
         if name != "mc_iqp_relinearise_batch":
             return fn
 
@@ -158,7 +174,9 @@ def test_iqp_batch_grows_its_buffers_when_a_resampled_track_does_not_fit(fake, m
     nv = torch.rand((B, n, 2), dtype=torch.float64)
     h = torch.ones((B, n), dtype=torch.float64)
     res = B_.iqp_batch(rt, nv, h, 0.12, 2.0, 3.0, iters_min=2, curv_error_allowed=0.01)
-    assert state["calls"] == 2 and state["caps"][1] == state["caps"][0] + 40 + 64          # grown, then accepted
+    # grown, then accepted; the third launch follows the iteration in which every track finished (the host learns that from
+    # the same single read as the point counts, so the launch is already queued: its kernels skip inactive tracks)
+    assert state["calls"] == 3 and state["caps"][1] == state["caps"][0] + 40 + 64 and state["caps"][2] == state["caps"][1]
     cap = state["caps"][1]
     assert res["alpha"].shape == (B, cap) and res["reftrack"].shape == (B, cap, 4) and res["normvec"].shape == (B, cap, 2)
     assert res["outer_iters"].tolist() == [2, 2] and res["n_pts"].tolist() == [cap - 5, cap - 5] and res["qp_solves"] == 4

@@ -241,3 +241,32 @@ def test_raceline_batch_properties_at_baseline_size():
         assert np.abs(d - el[:-1]).max() < 0.15                              # chord ~ arc (15-point polyline lengths) at 2 m steps
         kap = rl["kappa"][b, :m].cpu().numpy()
         assert np.abs(kap).max() < 0.5
+
+
+def test_band_truncation_on_a_strongly_non_uniform_track():
+    """The band of H (half-bandwidth 32) and the warm-up recurrences were validated on equidistant tracks; here the point
+    spacing varies 1 : 5 along the track (what a raw, un-resampled track or the mintime re-optimisation branch,
+    /root/reference/main_globaltraj.py:319-350, feeds through calc_splines(use_dist_scaling=True)).  The decay of Tri^-1
+    -- and with it the truncation error -- depends on the spacing ratios, so this is checked against the dense oracle."""
+    rng = np.random.default_rng(5)
+    fine = synth.make_track(21, 1200)                       # 3 m spacing
+    keep, i = [], 0
+    while i < fine.shape[0]:                                # alternate stretches of 1-point and 5-point steps (3 m / 15 m)
+        step = 5 if (len(keep) // 12) % 2 else 1
+        keep.append(i)
+        i += step
+    rt = fine[keep]
+    n = rt.shape[0]
+    assert 300 <= n <= 420
+    el = np.linalg.norm(np.diff(np.vstack((rt[:, :2], rt[0, :2])), axis=0), axis=1)
+    assert el.max() / el.min() > 4.5
+    path = _closed(rt)
+    cx, cy, M, nv = tph.calc_splines.calc_splines(path=path)
+    ocx, ocy, oA, onv = T.calc_splines(path)
+    assert np.abs(cx - ocx).max() < 1e-8 and np.abs(nv - onv).max() < 1e-10
+    alpha, cerr = tph.opt_min_curv.opt_min_curv(reftrack=rt, normvectors=nv, A=M, kappa_bound=0.12, w_veh=2.0)
+    oalpha, ocerr = T.opt_min_curv(rt, onv, oA, 0.12, 2.0)
+    err = rel_max(alpha, oalpha)
+    print(f"non-uniform track N={n}, spacing ratio {el.max() / el.min():.1f}: alpha rel err {err:.2e}")
+    assert err <= ALPHA_TOL
+    assert abs(cerr - ocerr) <= 1e-3 * ocerr + 1e-7
