@@ -6,7 +6,7 @@
 """
 from . import (batch, calc_ax_profile, calc_head_curv_an, check_normals_crossing, calc_splines, calc_t_profile,  # noqa: F401
                calc_vel_profile, create_raceline, import_veh_dyn_info, iqp_handler, opt_min_curv,
-               opt_shortest_path, synth)
+               opt_shortest_path, spline_approximation, synth)
 from . import globaltraj, helper_funcs_glob  # noqa: F401
 from .spline_system import SplineSystem  # noqa: F401
 

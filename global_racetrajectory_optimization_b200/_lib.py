@@ -54,6 +54,9 @@ _SIGS = {
     "mc_traj_extrema_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_dbl, _c_dbl, _vp, _vp]),
     "mc_assemble_trajectory_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp]),
     "mc_check_normals_crossing_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp]),
+    "mc_prep_track_workspace_bytes": (_sz, [_c_int, _c_int, _c_int]),
+    "mc_prep_track_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_dbl, _c_int, _c_int, _vp, _vp, _vp,
+                                     _vp, _sz, _vp]),
     "mc_polygon_length_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _c_int, _vp, _vp, _c_int, _c_dbl, _vp, _vp]),
     "mc_jitter_widths_batch": (_c_int, [_c_int, _c_int, _vp, _c_int, _vp, _vp, _vp, _c_dbl, _vp, _vp, _vp]),
     "mc_debug_read_profile": (_c_int, [_vp, _c_int]),

@@ -775,3 +775,59 @@ def jitter_widths_batch(base: torch.Tensor, seeds: torch.Tensor, rel: float = 0.
                                     _ptr(seeds), float(rel), _ptr(out), _ptr(n_out), _stream())
     _lib.check(rc, "mc_jitter_widths_batch")
     return out, n_out
+
+
+# ------------------------------------------------------------------------------------------------
+# prep_track front end: tph.spline_approximation + min-width inflation + splines + normals check
+# ------------------------------------------------------------------------------------------------
+@_device_guard
+def spline_approximation_batch(track: torch.Tensor, k_reg: int = 3, s_reg: float = 10.0, stepsize_prep: float = 1.0,
+                               stepsize_reg: float = 3.0, n_raw: Optional[torch.Tensor] = None,
+                               min_width: Optional[float] = None):
+    """Batched tph.spline_approximation (+ prep_track's min-width inflation) for imported tracks [B, n_raw_max, 4]
+    (unclosed; n_raw[b] points each).  Returns (reftrack_interp [B, n_out_max, 4], n_pts [B], smoothing_lambda [B]).
+    The smoothing spline is the Reinsch formulation with residual budget s_reg (csrc/prep_track.cu)."""
+    _require_cuda()
+    lib = _lib.load()
+    track = _f64(track, "track")
+    B, n_raw_max, four = track.shape
+    if four != 4:
+        raise ValueError("track must be [B, n_raw_max, 4]")
+    dev = track.device
+    n_raw = _npts(n_raw, B, dev)
+    length = float(_closed_polygon_length(track, n_raw).max().item())
+    n_int_max = int(math.ceil(length / float(stepsize_prep))) + 8
+    n_out_max = int(math.ceil(1.05 * length / float(stepsize_reg))) + 16
+    while True:
+        out = torch.zeros((B, n_out_max, 4), dtype=torch.float64, device=dev)
+        n_out = torch.zeros((B,), dtype=torch.int32, device=dev)
+        lam = torch.zeros((B,), dtype=torch.float64, device=dev)
+        ws = _workspace("prep_track", lib.mc_prep_track_workspace_bytes(B, n_raw_max, n_int_max), dev)
+        rc = lib.mc_prep_track_batch(B, n_raw_max, _ptr(n_raw), _ptr(track), int(k_reg), float(s_reg), float(stepsize_prep),
+                                     float(stepsize_reg), float(min_width) if min_width is not None else 0.0, n_int_max,
+                                     n_out_max, _ptr(out), _ptr(n_out), _ptr(lam), _ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, "mc_prep_track_batch")
+        need = int((-n_out).max().item())
+        if need <= 0:
+            return out, n_out, lam
+        n_out_max = max(n_out_max, need + 16)          # (a curve longer than 1.05 x its polygon, or a tiny capacity)
+        n_int_max = max(n_int_max, need + 16)
+
+
+def prep_track_batch(track: torch.Tensor, reg_smooth_opts: dict, stepsize_opts: dict, n_raw: Optional[torch.Tensor] = None,
+                     min_width: Optional[float] = None, check_normals: bool = True) -> dict:
+    """Batched helper_funcs_glob.src.prep_track.prep_track (/root/reference/helper_funcs_glob/src/prep_track.py): smoothing
+    and re-sampling, closed splines of the result, check of the normals, min-width inflation.  Returns dict(reftrack_interp,
+    n_pts, normvec_normalized_interp, h (the spline system in moment form), coeffs_x_interp, coeffs_y_interp,
+    normals_crossing [B] bool)."""
+    rt, n_pts, lam = spline_approximation_batch(track, k_reg=reg_smooth_opts["k_reg"], s_reg=reg_smooth_opts["s_reg"],
+                                                stepsize_prep=stepsize_opts["stepsize_prep"],
+                                                stepsize_reg=stepsize_opts["stepsize_reg"], n_raw=n_raw, min_width=None)
+    cx, cy, nv, h = calc_splines_batch(rt, n_pts=n_pts)
+    crossing = check_normals_crossing_batch(rt, nv, 10, n_pts=n_pts) if check_normals else None
+    if min_width is not None:                     # (the reference inflates AFTER the normals check: prep_track.py:89-98)
+        rt, n_pts, lam = spline_approximation_batch(track, k_reg=reg_smooth_opts["k_reg"], s_reg=reg_smooth_opts["s_reg"],
+                                                    stepsize_prep=stepsize_opts["stepsize_prep"],
+                                                    stepsize_reg=stepsize_opts["stepsize_reg"], n_raw=n_raw, min_width=min_width)
+    return dict(reftrack_interp=rt, n_pts=n_pts, normvec_normalized_interp=nv, h=h, coeffs_x_interp=cx, coeffs_y_interp=cy,
+                normals_crossing=crossing, smoothing_lambda=lam)

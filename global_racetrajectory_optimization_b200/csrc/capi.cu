@@ -55,6 +55,9 @@ void launch_traj_extrema(int, int, const int32_t *, const double *, const double
 void launch_assemble_trajectory(int, int, const int32_t *, const double *, const double *, const double *, const double *,
                                 const double *, const double *, int, const int32_t *, const double *, double *, cudaStream_t);
 void launch_normals_crossing(int, int, const int32_t *, const double *, const double *, int, int32_t *, cudaStream_t);
+size_t prep_track_ws_doubles(int, int);
+void launch_prep_track(int, int, const int32_t *, const double *, double, double, double, double, int, int, double *, int32_t *,
+                       double *, double *, cudaStream_t);
 void launch_polygon_length(int, int, const int32_t *, const double *, int, const double *, const double *, int, double, double *,
                            cudaStream_t);
 void launch_jitter_widths(int, int, const int32_t *, int, const double *, const int32_t *, const int64_t *, double, double *,
@@ -465,6 +468,28 @@ int mc_check_normals_crossing_batch(int B, int n_max, const int32_t *n_pts, cons
         return bad("mc_check_normals_crossing_batch: bad argument");
     mc::launch_normals_crossing(B, n_max, n_pts, track, normvec, horizon, crossing, (cudaStream_t)stream);
     return check_cuda("normals_crossing_kernel");
+}
+
+size_t mc_prep_track_workspace_bytes(int B, int n_raw_max, int n_int_max) {
+    if (B <= 0 || n_raw_max < 5 || n_int_max < 6) return 0;
+    return align256((size_t)B * mc::prep_track_ws_doubles(n_raw_max, n_int_max) * sizeof(double));
+}
+
+int mc_prep_track_batch(int B, int n_raw_max, const int32_t *n_raw, const double *track, int k_reg, double s_reg,
+                        double stepsize_prep, double stepsize_reg, double min_width, int n_int_max, int n_out_max,
+                        double *reftrack_interp, int32_t *n_out, double *smoothing_lambda, void *workspace,
+                        size_t workspace_bytes, void *stream) {
+    if (B <= 0 || n_raw_max < 5 || !track || !(s_reg > 0.0) || !(stepsize_prep > 0.0) || !(stepsize_reg > 0.0) || n_int_max < 6 ||
+        n_out_max < 4 || !reftrack_interp || !n_out)
+        return bad("mc_prep_track_batch: bad argument");
+    if (k_reg != 3) return bad("mc_prep_track_batch: only cubic splines (k_reg = 3, the reference's setting) are implemented");
+    if (!workspace || workspace_bytes < mc_prep_track_workspace_bytes(B, n_raw_max, n_int_max)) {
+        snprintf(g_err, sizeof(g_err), "mc_prep_track_batch: workspace too small");
+        return MC_EWORKSPACE;
+    }
+    mc::launch_prep_track(B, n_raw_max, n_raw, track, s_reg, stepsize_prep, stepsize_reg, min_width, n_int_max, n_out_max,
+                          reftrack_interp, n_out, smoothing_lambda, (double *)workspace, (cudaStream_t)stream);
+    return check_cuda("prep_track_kernel");
 }
 
 int mc_polygon_length_batch(int B, int n_max, const int32_t *n_pts, const double *pts, int stride, const double *normvec,

@@ -268,3 +268,19 @@ def check_normals_crossing(track: np.ndarray, normvec_normalized: np.ndarray, ho
         print("WARNING: Horizon of %i points makes no sense for a track with %i points, reduce horizon!"
               % (horizon, no_points))
     return bool(_b.check_normals_crossing_batch(_up(track), _up(normvec_normalized), int(horizon))[0].item())
+
+
+def spline_approximation(track: np.ndarray, k_reg: int = 3, s_reg: int = 10, stepsize_prep: float = 1.0,
+                         stepsize_reg: float = 3.0, debug: bool = False) -> np.ndarray:
+    """tph.spline_approximation.spline_approximation -> track_reg [n, 4] (unclosed), call site
+    /root/reference/helper_funcs_glob/src/prep_track.py:39-45.  Same statements on the device, with the Reinsch smoothing
+    spline (residual budget s_reg) in place of scipy's FITPACK splprep (csrc/prep_track.cu)."""
+    track = np.asarray(track, dtype=np.float64)
+    if track.ndim != 2 or track.shape[1] != 4:
+        raise ValueError("track must be an [n, 4] array [x, y, w_tr_right, w_tr_left]")
+    out, n_out, lam = _b.spline_approximation_batch(_up(track), k_reg=int(k_reg), s_reg=float(s_reg),
+                                                    stepsize_prep=float(stepsize_prep), stepsize_reg=float(stepsize_reg))
+    res = out[0, :int(n_out[0].item())].cpu().numpy()
+    if debug:
+        print("Spline approximation: smoothing parameter %.3e, %i points" % (float(lam[0].item()), res.shape[0]))
+    return res

@@ -294,6 +294,24 @@ int mc_jitter_widths_batch(int V, int n_max, const int32_t *n_pts_base, int n_ba
                            const int32_t *centre_id, const int64_t *seed, double rel, double *out, int32_t *n_pts_out,
                            void *stream);
 
+/* -------------------------------------------------------------------------------------------------
+ * tph.spline_approximation.spline_approximation(track, k_reg, s_reg, stepsize_prep, stepsize_reg) followed by prep_track's
+ * min-width inflation -- call sites /root/reference/helper_funcs_glob/src/prep_track.py:39-45 and :89-98.
+ * Every statement of tph.spline_approximation is kept except scipy's splprep (FITPACK), which is replaced by the periodic
+ * cubic smoothing spline of Reinsch with the same residual budget s_reg (see csrc/prep_track.cu; the distance to the
+ * FITPACK route is reported by tests/test_gpu_prep.py).
+ *   track [B][n_raw_max][4]       : imported tracks x, y, w_tr_right, w_tr_left (unclosed), n_raw[b] points each
+ *   n_int_max                     : capacity for the pre-interpolated closed track (>= ceil(length / stepsize_prep) + 1)
+ *   min_width                     : <= 0 => no inflation (prep_track's min_width=None)
+ *   reftrack_interp [B][n_out_max][4], n_out [B]: the prepared tracks; n_out[b] = -(points needed) if a capacity is too small
+ *   smoothing_lambda [B] or NULL  : the smoothing parameter found for every track
+ */
+size_t mc_prep_track_workspace_bytes(int B, int n_raw_max, int n_int_max);
+int mc_prep_track_batch(int B, int n_raw_max, const int32_t *n_raw, const double *track, int k_reg, double s_reg,
+                        double stepsize_prep, double stepsize_reg, double min_width, int n_int_max, int n_out_max,
+                        double *reftrack_interp, int32_t *n_out, double *smoothing_lambda, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
 /* Length [B] of the closed polygon through the first n_pts[b] points of every track; with normvec and shift the points are
  * p_i + sign * shift_i * n_i (shift: alpha [B][n_max] with shift_stride 1, or a width column &track[0][0][2] with
  * shift_stride 4).  Used by the host to size the re-sampling buffers of create_raceline / interp_track / iqp_handler. */
