@@ -810,6 +810,9 @@ def spline_approximation_batch(track: torch.Tensor, k_reg: int = 3, s_reg: float
         need = int((-n_out).max().item())
         if need <= 0:
             return out, n_out, lam
+        if need + 16 <= min(n_out_max, n_int_max):     # the kernel refused for another reason than capacity
+            raise ValueError("spline_approximation_batch: a track is too short to be smoothed (fewer than 5 points after "
+                             "pre-interpolation)")
         n_out_max = max(n_out_max, need + 16)          # (a curve longer than 1.05 x its polygon, or a tiny capacity)
         n_int_max = max(n_int_max, need + 16)
 

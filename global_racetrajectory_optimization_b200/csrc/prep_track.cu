@@ -45,48 +45,67 @@ __device__ inline void pt_eval(const PtSpline &s, double t, double *x, double *y
 // sides, by a bordered LDL^T: chain 0..n-3, separator = the last two nodes.  Sequential: run by ONE thread.
 __device__ void penta_cyclic_solve2(int n, const double *a0, const double *a1, const double *a2, const double *bx, const double *by,
                                     double *d, double *l1, double *l2, double *g0, double *g1, double *x, double *y) {
+    // (recurrence state is carried in registers: the loads of an iteration never depend on the previous iteration's stores,
+    //  so the unrolled loops keep several of them in flight)
     const int m = n - 2;
-    d[0] = a0[0]; l1[0] = 0.0; l2[0] = 0.0;
-    l1[1] = a1[0] / d[0]; l2[1] = 0.0;
-    d[1] = a0[1] - l1[1] * l1[1] * d[0];
+    double dm2 = a0[0];
+    d[0] = dm2; l1[0] = 0.0; l2[0] = 0.0;
+    double l1m1 = a1[0] / dm2;
+    double dm1 = a0[1] - l1m1 * l1m1 * dm2;
+    l1[1] = l1m1; l2[1] = 0.0; d[1] = dm1;
+#pragma unroll 4
     for (int k = 2; k < m; ++k) {
-        l2[k] = a2[k - 2] / d[k - 2];
-        l1[k] = (a1[k - 1] - l2[k] * l1[k - 1] * d[k - 2]) / d[k - 1];
-        d[k] = a0[k] - l1[k] * l1[k] * d[k - 1] - l2[k] * l2[k] * d[k - 2];
+        const double l2k = a2[k - 2] / dm2;
+        const double l1k = (a1[k - 1] - l2k * l1m1 * dm2) / dm1;
+        const double dk = a0[k] - l1k * l1k * dm1 - l2k * l2k * dm2;
+        l2[k] = l2k; l1[k] = l1k; d[k] = dk;
+        dm2 = dm1; dm1 = dk; l1m1 = l1k;
     }
     // Y = A[sep, chain]: node m couples to m-2 (a2), m-1 (a1) and across the wrap to 0 (a2[m]); node m+1 to m-1 (a2) and to 0 (a1), 1 (a2)
-    for (int k = 0; k < m; ++k) {
-        double y0 = 0.0, y1 = 0.0;
-        if (k == m - 2) y0 += a2[m - 2];
-        if (k == m - 1) { y0 += a1[m - 1]; y1 += a2[m - 1]; }
-        if (k == 0) { y0 += a2[m]; y1 += a1[m + 1]; }
-        if (k == 1) y1 += a2[m + 1];
-        double v0 = y0, v1 = y1;
-        if (k >= 1) { v0 -= g0[k - 1] * l1[k]; v1 -= g1[k - 1] * l1[k]; }
-        if (k >= 2) { v0 -= g0[k - 2] * l2[k]; v1 -= g1[k - 2] * l2[k]; }
-        g0[k] = v0; g1[k] = v1;
-    }
     double s00 = a0[m], s01 = a1[m], s11 = a0[m + 1];
-    for (int k = 0; k < m; ++k) { const double w = 1.0 / d[k]; s00 -= g0[k] * g0[k] * w; s01 -= g0[k] * g1[k] * w; s11 -= g1[k] * g1[k] * w; }
+    {
+        double p0 = 0.0, p1 = 0.0, pp0 = 0.0, pp1 = 0.0;        // g[k-1], g[k-2]
+#pragma unroll 4
+        for (int k = 0; k < m; ++k) {
+            double y0 = 0.0, y1 = 0.0;
+            if (k == m - 2) y0 += a2[m - 2];
+            if (k == m - 1) { y0 += a1[m - 1]; y1 += a2[m - 1]; }
+            if (k == 0) { y0 += a2[m]; y1 += a1[m + 1]; }
+            if (k == 1) y1 += a2[m + 1];
+            const double c1 = l1[k], c2 = l2[k];
+            const double v0 = y0 - p0 * c1 - pp0 * c2, v1 = y1 - p1 * c1 - pp1 * c2;
+            g0[k] = v0; g1[k] = v1;
+            const double w = 1.0 / d[k];
+            s00 -= v0 * v0 * w; s01 -= v0 * v1 * w; s11 -= v1 * v1 * w;
+            pp0 = p0; pp1 = p1; p0 = v0; p1 = v1;
+        }
+    }
     const double det = s00 * s11 - s01 * s01;
     for (int r = 0; r < 2; ++r) {
         const double *b = r ? by : bx;
         double *xx = r ? y : x;
-        for (int k = 0; k < m; ++k) {            // forward (result in xx)
-            double v = b[k];
-            if (k >= 1) v -= l1[k] * xx[k - 1];
-            if (k >= 2) v -= l2[k] * xx[k - 2];
-            xx[k] = v;
-        }
         double b0 = b[m], b1 = b[m + 1];
-        for (int k = 0; k < m; ++k) { const double z = xx[k] / d[k]; b0 -= g0[k] * z; b1 -= g1[k] * z; }
+        {
+            double p = 0.0, pp = 0.0;
+#pragma unroll 4
+            for (int k = 0; k < m; ++k) {            // forward (result in xx)
+                const double v = b[k] - l1[k] * p - l2[k] * pp;
+                xx[k] = v;
+                const double z = v / d[k];
+                b0 -= g0[k] * z; b1 -= g1[k] * z;
+                pp = p; p = v;
+            }
+        }
         const double xs0 = (s11 * b0 - s01 * b1) / det, xs1 = (s00 * b1 - s01 * b0) / det;
         xx[m] = xs0; xx[m + 1] = xs1;
+        double n1 = 0.0, n2 = 0.0, c1 = 0.0, c2a = 0.0, c2b = 0.0;      // x[k+1], x[k+2]; l1[k+1], l2[k+2] (as seen from k), l2[k+1]
+#pragma unroll 4
         for (int k = m - 1; k >= 0; --k) {
-            double v = (xx[k] - g0[k] * xs0 - g1[k] * xs1) / d[k];
-            if (k + 1 < m) v -= l1[k + 1] * xx[k + 1];
-            if (k + 2 < m) v -= l2[k + 2] * xx[k + 2];
+            const double v = (xx[k] - g0[k] * xs0 - g1[k] * xs1) / d[k] - c1 * n1 - c2a * n2;
             xx[k] = v;
+            n2 = n1; n1 = v;
+            c2a = c2b;               // l2[k+1] becomes the l2[(k-1)+2] of the next step
+            c1 = l1[k]; c2b = l2[k];
         }
     }
 }
@@ -278,7 +297,6 @@ prep_track_kernel(int n_raw_max, const int32_t *__restrict__ n_raw_b, const doub
         const double sgn = (cr > 0.0) ? 1.0 : (cr < 0.0) ? -1.0 : 0.0;
         const double dst = wr[i];
         wl[i] = tr[4 * i0 + 3] - sgn * dst;
-        __syncwarp();
         wr[i] = tr[4 * i0 + 2] + sgn * dst;
     }
     __syncthreads();
