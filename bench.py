@@ -354,9 +354,12 @@ def run_b200(args) -> dict:
     if cfg == "c1":
         pdip_ms, setup_ms = tm.mean_ms("pdip"), tm.mean_ms("setup")
         n_stations = float(res["n_out"].double().mean().item())
-        per_kernel = [_k("calc_splines_kernel", 96.0 * n, tm.mean_ms("splines"), bl),
+        # the two streaming kernels run ~0.1 ms per launch: inside the step their event pairs also span the wrapper's output
+        # allocations and launch gaps, so they are timed here as back-to-back launches with pre-allocated outputs
+        spl_ms, rl_ms = streaming_kernel_times(torch, B_, lib, _lib, rt, res["alpha"], n, W["n_out_max"], dev)
+        per_kernel = [_k("calc_splines_kernel (normals + h out; back-to-back launches)", 32.0 * n + 24.0 * n, spl_ms, bl),
                       _k("mincurv_setup_kernel + mincurv_pdip_kernel", ALG_BYTES_PER_POINT_K2 * n, setup_ms + pdip_ms, bl),
-                      _k("create_raceline_kernel (+ psi/kappa)", 40.0 * n + 40.0 * n_stations, tm.mean_ms("raceline"), bl)]
+                      _k("create_raceline_kernel (+ psi/kappa; back-to-back launches)", 40.0 * n + 64.0 * n + 40.0 * n_stations + 8.0 * n, rl_ms, bl)]
         alg_bytes = ALG_BYTES_PER_POINT_K2 * n * bl
         achieved = alg_bytes / (pdip_ms * 1e-3) / 1e9
         per_qp, tsrc = measured_traffic()
@@ -415,6 +418,42 @@ def run_b200(args) -> dict:
     if world > 1:
         dist.destroy_process_group()
     return line if rank == 0 else None
+
+
+def streaming_kernel_times(torch, B_, lib, _lib, rt, alpha, n, n_out_max, dev, reps: int = 6):
+    """Mean duration [ms] of calc_splines_kernel and create_raceline_kernel: `reps` launches each through the C-ABI, queued
+    back to back between two CUDA events, outputs pre-allocated (inputs: the bench batch, larger than L2 together with
+    the outputs)."""
+    p, s = B_._ptr, B_._stream()
+    Bq = rt.shape[0]
+    f64 = dict(dtype=torch.float64, device=dev)
+    nv, h = torch.empty((Bq, n, 2), **f64), torch.empty((Bq, n), **f64)
+    ws = B_._workspace("splines", lib.mc_calc_splines_workspace_bytes(Bq, n), dev)
+
+    def spl():
+        _lib.check(lib.mc_calc_splines_batch(Bq, n, None, p(rt), 4, None, 1, None, None, p(nv), p(h), p(ws), ws.numel(), s), "splines")
+    o = dict(cx=torch.empty((Bq, n, 4), **f64), cy=torch.empty((Bq, n, 4), **f64), sl=torch.empty((Bq, n), **f64),
+             n_out=torch.empty((Bq,), dtype=torch.int32, device=dev), ri=torch.empty((Bq, n_out_max, 2), **f64),
+             si=torch.empty((Bq, n_out_max), dtype=torch.int32, device=dev), tv=torch.empty((Bq, n_out_max), **f64),
+             ss=torch.empty((Bq, n_out_max), **f64), el=torch.empty((Bq, n_out_max), **f64), psi=torch.empty((Bq, n_out_max), **f64),
+             kap=torch.empty((Bq, n_out_max), **f64))
+
+    def rl():
+        _lib.check(lib.mc_create_raceline_batch(Bq, n, None, p(rt), 4, p(nv), p(alpha), STEP_INTERP, n_out_max, p(o["cx"]), p(o["cy"]),
+                                                p(o["sl"]), p(o["n_out"]), p(o["ri"]), p(o["si"]), p(o["tv"]), p(o["ss"]), p(o["el"]),
+                                                p(o["psi"]), p(o["kap"]), p(ws), ws.numel(), s), "raceline")
+    out = []
+    for fn in (spl, rl):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        out.append(a.elapsed_time(b) / reps)
+    return out[0], out[1]
 
 
 def run_e2e(args, W, torch, B_, dev, world, sync_all, dist) -> dict:

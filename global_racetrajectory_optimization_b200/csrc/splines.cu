@@ -17,30 +17,83 @@ enum SVec : int { S_H = 0, S_DG, S_DFW, S_DBW, S_LFW, S_INVD, S_R0, S_R1, S_Y0, 
 __host__ __device__ inline int spl_np(int n_max) { return ((n_max + 31) / 32) * 32 + 32; }
 size_t spline_ws_doubles(int n_max) { return (size_t)S_NUM * spl_np(n_max); }
 
-// moments + coefficients of the closed spline through (PX, PY) with parameter scales H (all in scratch)
-__device__ void closed_spline(double *sv, int np, int n, double *__restrict__ cx, double *__restrict__ cy,
+// ---------------------------------------------------------------------------------------------
+// Closed spline through (PX, PY) with parameter scales H: moments by the periodic tridiagonal LDL^T of common.cuh's
+// scheme (every thread runs the recurrences over a chunk of TRI_CHUNK points after a warm-up of TRI_WARM points), here on
+// EIGHT vectors that live in shared memory whenever the track fits (n_max <= ~3400 points): H, PX, PY (inputs), INVD,
+// Y0, Y1, MX, MY.  Diagonal, sub-diagonal factors and right-hand sides are formed on the fly from H / PX / PY instead of
+// being staged through further vectors.  (The first version kept fifteen scratch vectors per track in global memory:
+// 127 KB per track, 300 MB for the bench batch -- 6.9 % of the HBM roofline.)
+// ---------------------------------------------------------------------------------------------
+constexpr int SPL_SM_VECS = 8;
+__host__ __device__ inline size_t spline_smem_bytes(int n_max) { return (size_t)SPL_SM_VECS * spl_np(n_max) * sizeof(double); }
+constexpr size_t SPL_SMEM_LIMIT = 220 * 1024;
+
+__device__ void closed_spline(double *sm, int np, int n, double *__restrict__ cx, double *__restrict__ cy,
                               double *__restrict__ nvec) {
-    double *H = sv + S_H * np, *DG = sv + S_DG * np, *DFW = sv + S_DFW * np, *DBW = sv + S_DBW * np;
-    double *LFW = sv + S_LFW * np, *INVD = sv + S_INVD * np, *R0 = sv + S_R0 * np, *R1 = sv + S_R1 * np;
-    double *Y0 = sv + S_Y0 * np, *Y1 = sv + S_Y1 * np, *MX = sv + S_MX * np, *MY = sv + S_MY * np;
-    const double *PX = sv + S_PX * np, *PY = sv + S_PY * np;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int im1 = (i == 0) ? n - 1 : i - 1;
-        DG[i] = 2.0 * (H[im1] + H[i]);
+    const double *H = sm, *PX = sm + np, *PY = sm + 2 * np;
+    double *INVD = sm + 3 * np, *Y0 = sm + 4 * np, *Y1 = sm + 5 * np, *MX = sm + 6 * np, *MY = sm + 7 * np;
+    // ---- forward pivots d_i = 2 (h_{i-1} + h_i) - h_{i-1}^2 / d_{i-1}; stored as 1 / d_i ----
+    for (int c0 = threadIdx.x * TRI_CHUNK; c0 < n; c0 += blockDim.x * TRI_CHUNK) {
+        const int c1 = min(c0 + TRI_CHUNK, n);
+        int i = wrapi(c0 - TRI_WARM, n);
+        double hm = H[(i == 0) ? n - 1 : i - 1], prev = 2.0 * (hm + H[i]);
+        hm = H[i];
+#pragma unroll 8
+        for (int s = 0; s < TRI_WARM - 1; ++s) {
+            i = (i + 1 == n) ? 0 : i + 1;
+            const double hi = H[i];
+            prev = 2.0 * (hm + hi) - hm * hm / prev;
+            hm = hi;
+        }
+        for (int s = c0; s < c1; ++s) {
+            i = (i + 1 == n) ? 0 : i + 1;
+            const double hi = H[i];
+            prev = 2.0 * (hm + hi) - hm * hm / prev;
+            hm = hi;
+            INVD[i] = 1.0 / prev;
+        }
     }
     __syncthreads();
-    tri_pivots(DG, H, DFW, DBW, n);
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int im1 = (i == 0) ? n - 1 : i - 1, ip1 = (i + 1 == n) ? 0 : i + 1;
-        const double hi = H[i], him = H[im1];
-        LFW[i] = him / DFW[im1];
-        INVD[i] = 1.0 / DFW[i];
-        R0[i] = 6.0 * ((PX[ip1] - PX[i]) / hi - (PX[i] - PX[im1]) / him);
-        R1[i] = 6.0 * ((PY[ip1] - PY[i]) / hi - (PY[i] - PY[im1]) / him);
+    // ---- forward substitution y_i = r_i - (h_{i-1} / d_{i-1}) y_{i-1},  r = 6 D2 p ----
+    for (int c0 = threadIdx.x * TRI_CHUNK; c0 < n; c0 += blockDim.x * TRI_CHUNK) {
+        const int c1 = min(c0 + TRI_CHUNK, n);
+        int i = wrapi(c0 - TRI_WARM, n);
+        int im = (i == 0) ? n - 1 : i - 1;
+        double yx = 0.0, yy = 0.0;
+        double hm = H[im], pxm = PX[im], pym = PY[im], pxi = PX[i], pyi = PY[i], idm = INVD[im];
+#pragma unroll 4
+        for (int s = 0; s < TRI_WARM + TRI_CHUNK; ++s) {
+            if (s >= TRI_WARM + (c1 - c0)) break;
+            const int ip = (i + 1 == n) ? 0 : i + 1;
+            const double hi = H[i], pxp = PX[ip], pyp = PY[ip];
+            const double rx = 6.0 * ((pxp - pxi) / hi - (pxi - pxm) / hm), ry = 6.0 * ((pyp - pyi) / hi - (pyi - pym) / hm);
+            const double l = hm * idm;
+            yx = rx - l * yx;
+            yy = ry - l * yy;
+            if (s >= TRI_WARM) { Y0[i] = yx; Y1[i] = yy; }
+            idm = INVD[i];
+            hm = hi; pxm = pxi; pym = pyi; pxi = pxp; pyi = pyp;
+            i = ip;
+        }
     }
     __syncthreads();
-    tri_solve2(LFW, INVD, H, R0, R1, Y0, Y1, MX, MY, n);
+    // ---- backward substitution m_i = (y_i - h_i m_{i+1}) / d_i ----
+    for (int c0 = threadIdx.x * TRI_CHUNK; c0 < n; c0 += blockDim.x * TRI_CHUNK) {
+        const int c1 = min(c0 + TRI_CHUNK, n);
+        int i = wrapi(c1 - 1 + TRI_WARM, n);
+        double mx = 0.0, my = 0.0;
+#pragma unroll 4
+        for (int s = 0; s < TRI_WARM + TRI_CHUNK; ++s) {
+            if (s >= TRI_WARM + (c1 - c0)) break;
+            const double o = H[i], id = INVD[i];
+            mx = (Y0[i] - o * mx) * id;
+            my = (Y1[i] - o * my) * id;
+            if (s >= TRI_WARM) { MX[i] = mx; MY[i] = my; }
+            i = (i == 0) ? n - 1 : i - 1;
+        }
+    }
+    __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int ip1 = (i + 1 == n) ? 0 : i + 1;
         const double h2 = H[i] * H[i];
@@ -70,8 +123,9 @@ calc_splines_kernel(int n_max, const int32_t *__restrict__ n_pts, const double *
     const int n = n_pts ? n_pts[b] : n_max;
     if (n < 3 || n > n_max) return;
     const int np = spl_np(n_max);
-    double *sv = ws + (size_t)b * S_NUM * np;
-    double *H = sv + S_H * np, *PX = sv + S_PX * np, *PY = sv + S_PY * np;
+    extern __shared__ __align__(16) double spl_sm[];
+    double *sv = (spline_smem_bytes(n_max) <= SPL_SMEM_LIMIT) ? spl_sm : ws + (size_t)b * S_NUM * np;
+    double *H = sv, *PX = sv + np, *PY = sv + 2 * np;
     const double *p = xy + (size_t)b * n_max * xy_stride;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int ip1 = (i + 1 == n) ? 0 : i + 1;
@@ -132,8 +186,9 @@ create_raceline_kernel(int n_max, const int32_t *__restrict__ n_pts, const doubl
     __shared__ double s_part[256];
     if (n < 3 || n > n_max) { if (threadIdx.x == 0) n_out[b] = 0; return; }
     const int np = spl_np(n_max);
-    double *sv = ws + (size_t)b * S_NUM * np;
-    double *H = sv + S_H * np, *PX = sv + S_PX * np, *PY = sv + S_PY * np, *CUM = sv + S_CUM * np;
+    extern __shared__ __align__(16) double spl_sm[];
+    double *sv = (spline_smem_bytes(n_max) <= SPL_SMEM_LIMIT) ? spl_sm : ws + (size_t)b * S_NUM * np;
+    double *H = sv, *PX = sv + np, *PY = sv + 2 * np, *CUM = sv + 4 * np;      // (CUM takes Y0's place after the spline)
     const double *p = refline + (size_t)b * n_max * ref_stride;
     const double *nv = normvec + (size_t)b * n_max * 2;
     const double *al = alpha + (size_t)b * n_max;
@@ -286,15 +341,19 @@ __global__ void scale_alpha_kernel(int n_max, double *__restrict__ alpha, const 
 void launch_calc_splines(int B, int n_max, const int32_t *n_pts, const double *xy, int xy_stride,
                          const double *el_lengths, int use_dist_scaling, double *cx, double *cy, double *nvec,
                          double *h_out, double *ws, cudaStream_t stream) {
-    calc_splines_kernel<<<B, 256, 0, stream>>>(n_max, n_pts, xy, xy_stride, el_lengths, use_dist_scaling, cx, cy, nvec,
-                                               h_out, ws);
+    const size_t sm = spline_smem_bytes(n_max) <= SPL_SMEM_LIMIT ? spline_smem_bytes(n_max) : 0;
+    cudaFuncSetAttribute(calc_splines_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPL_SMEM_LIMIT);
+    calc_splines_kernel<<<B, 256, sm, stream>>>(n_max, n_pts, xy, xy_stride, el_lengths, use_dist_scaling, cx, cy, nvec,
+                                                h_out, ws);
 }
 void launch_create_raceline(int B, int n_max, const int32_t *n_pts, const double *refline, int ref_stride,
                             const double *normvec, const double *alpha, double stepsize, int n_out_max, double *cx,
                             double *cy, double *sl, int32_t *n_out, double *ri, int32_t *si, double *tv, double *ss,
                             double *el, double *psi, double *kappa, double *ws, cudaStream_t stream) {
-    create_raceline_kernel<<<B, 256, 0, stream>>>(n_max, n_pts, refline, ref_stride, normvec, alpha, stepsize, n_out_max,
-                                                  cx, cy, sl, n_out, ri, si, tv, ss, el, psi, kappa, ws);
+    const size_t sm = spline_smem_bytes(n_max) <= SPL_SMEM_LIMIT ? spline_smem_bytes(n_max) : 0;
+    cudaFuncSetAttribute(create_raceline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPL_SMEM_LIMIT);
+    create_raceline_kernel<<<B, 256, sm, stream>>>(n_max, n_pts, refline, ref_stride, normvec, alpha, stepsize, n_out_max,
+                                                   cx, cy, sl, n_out, ri, si, tv, ss, el, psi, kappa, ws);
 }
 void launch_head_curv(int B, int n_max, const double *cx, const double *cy, int n_eval_max, const int32_t *n_eval,
                       const int32_t *ind, const double *t, double *psi, double *kappa, double *dkappa,
