@@ -357,9 +357,9 @@ def run_b200(args) -> dict:
         # the two streaming kernels run ~0.1 ms per launch: inside the step their event pairs also span the wrapper's output
         # allocations and launch gaps, so they are timed here as back-to-back launches with pre-allocated outputs
         spl_ms, rl_ms = streaming_kernel_times(torch, B_, lib, _lib, rt, res["alpha"], n, W["n_out_max"], dev)
-        per_kernel = [_k("calc_splines_kernel (normals + h out; back-to-back launches)", 32.0 * n + 24.0 * n, spl_ms, bl),
+        per_kernel = [_k("calc_splines_kernel (x, y in; normals + h out: 40 B/point; back-to-back launches)", 40.0 * n, spl_ms, bl),
                       _k("mincurv_setup_kernel + mincurv_pdip_kernel", ALG_BYTES_PER_POINT_K2 * n, setup_ms + pdip_ms, bl),
-                      _k("create_raceline_kernel (+ psi/kappa; back-to-back launches)", 40.0 * n + 64.0 * n + 40.0 * n_stations + 8.0 * n, rl_ms, bl)]
+                      _k("create_raceline_kernel (+ psi/kappa; 40 B in + 72 B coefficients/lengths per point, 60 B per station; back-to-back launches)", 112.0 * n + 60.0 * n_stations, rl_ms, bl)]
         alg_bytes = ALG_BYTES_PER_POINT_K2 * n * bl
         achieved = alg_bytes / (pdip_ms * 1e-3) / 1e9
         per_qp, tsrc = measured_traffic()
