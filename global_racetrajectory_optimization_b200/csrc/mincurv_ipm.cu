@@ -35,13 +35,20 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int IP_THREADS = 64;
 constexpr int SUB = 8;                 // columns per hand-off / streaming unit
 constexpr int VBP = 12;                // pitch of the row-major panel buffers (conflict-free DMMA fragment loads, 16-byte rows)
-constexpr int FROW = 34;               // HBM (and sweep-ring) pitch of a factor row: [l or g (32), t or z, w]
+constexpr int FROW = 34;               // pitch of a fill row: [g (32), z, w]
 constexpr int HB_SLOTS = 2;            // band-row units of warp 0 (the next panel's is in flight)
 constexpr int HO_SLOTS = 2;            // panels between warp 0 and warp 1
-constexpr int RING_UNITS = 7;          // sweep ring: 32-row window (5 units) + 2 units of prefetch
-constexpr int RING_UNIT_DOUBLES = SUB * FROW;         // 272
+constexpr int LROW = 42;               // pitch of a chain-factor row: [Q - I (8), L21 (32), t, w]
+#ifndef MC_LT_SLOTS
+#define MC_LT_SLOTS 3
+#endif
+constexpr int LT_SLOTS = MC_LT_SLOTS;  // sweep rings: warp 0 streams the chain rows (LT), warp 1 the fill rows (GT), concurrently
+constexpr int GT_SLOTS = 6 - LT_SLOTS;
+constexpr int RING_UNITS = LT_SLOTS + GT_SLOTS;       // mbarriers: [0, LT_SLOTS) warp 0, [LT_SLOTS, RING_UNITS) warp 1
+constexpr int QDEPTH = 16;             // units of z (forward) / t (backward) in flight between the two warps
+constexpr int LT_UNIT_DOUBLES = SUB * LROW;           // 336
+constexpr int GT_UNIT_DOUBLES = SUB * FROW;           // 272
 constexpr unsigned HB_UNIT_BYTES = SUB * HB_PITCH * sizeof(double);   // 2176
-constexpr unsigned FUNIT_BYTES = SUB * FROW * sizeof(double);         // 2176
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -155,7 +162,11 @@ struct IpShared {
             Handoff ho[HO_SLOTS];                     // warp 0 -> warp 1
             double gb[32 * VBP];                      // warp 1: the panel of the fill rows, row-major (DMMA fragments)
         } f;
-        double ring[RING_UNITS][RING_UNIT_DOUBLES];   // sweeps: streamed factor units
+        struct {
+            double lt[LT_SLOTS][LT_UNIT_DOUBLES];     // sweeps: streamed chain units (warp 0)
+            double gt[GT_SLOTS][GT_UNIT_DOUBLES];     //         streamed fill units (warp 1)
+            double q[QDEPTH * SUB];                   //         z (forward) / t (backward) handed between the warps
+        } sw;
         double win[hband_win_doubles(IP_THREADS)];    // K2b': scratch of the weighted band assembly
     } u;
     union {
@@ -165,15 +176,19 @@ struct IpShared {
     double wS[32], gs[32], part[2][32];
     double red[32];
     uint64_t hb_full[HB_SLOTS], ho_full[HO_SLOTS], ho_empty[HO_SLOTS], ring_full[RING_UNITS];
-    unsigned ring_phase;                              // parity bit per ring slot
+    unsigned ring_phase[2];                           // parity bit per ring slot, one word per warp
+    int prog[4];                                      // sweep progress (units done): forward w0, w1; backward w0, w1
     int flag;
     int next;                                         // next instance index (dynamic work distribution)
 };
 
-// pointers into the instance slab that the factorisation and the sweeps use.  Factor rows in HBM (pitch 34 doubles, so
-// that a unit of eight rows is one 2176-byte bulk copy and every row is 16-byte aligned):
-//   LT[k] = [ L[k+1 .. k+32][k],  t_k,  w_k ]      t = (y - G^T x_S) w: right-hand side of the backward sweep, w = 1/d_k
-//   GT[k] = [ G[0 .. 31][k],      z_k,  w_k ]      z = w y: what the separator's forward substitution needs
+// pointers into the instance slab that the factorisation and the sweeps use.  Factor rows in HBM, one bulk copy per unit
+// of eight rows (every row 16-byte aligned):
+//   LT[k0+j] = [ (Q - I)[0..7][j], L21[0..31][j], -, w_k ]   (pitch 42) the chain factor, one panel of columns k0 .. k0+7
+//              at a time: L21 = the 32 rows of L below the panel, Q = L11^-1 the inverse of the panel's unit-lower block, so
+//              that the panel's triangular solve in the sweeps is a mat-vec too (forward: y1 = Q a1, a2 -= L21 y1;
+//              backward: u = t1 - L21^T x2, x1 = Q^T u).  t = (y - G^T x_S) w: right-hand side of the backward sweep, w = 1/d_k
+//   GT[k]    = [ G[0 .. 31][k],  z_k,  w_k ]                  (pitch 34) z = w y: what the separator's forward part needs
 // so the sweeps read nothing but the streamed units (no per-column global loads on the serial chains).  Columns
 // NA .. 8 ceil(NA / 8) - 1 are padding (pivot 1, nothing else): every unit is a full panel.
 struct Factor {
@@ -188,7 +203,7 @@ __device__ __forceinline__ Factor make_factor(double *slab, const Layout &L, int
     F.HB = slab + L.o_hb;
     F.DD = vec(slab, L, V_DD);
     F.LT = slab + L.o_tiles;
-    F.GT = F.LT + (size_t)L.np * FROW;
+    F.GT = F.LT + (size_t)L.np * LROW;
     F.n = n;
     F.NA = n - 32;
     return F;
@@ -273,7 +288,7 @@ __device__ __noinline__ bool factor_chain(IpShared &sh, const double *__restrict
         SEG(10);
         // ---- (2) the panel ----
         double dsave = 1.0, wsave = 1.0, ysave = 0.0;
-        double *ltp = LTp + (size_t)k0 * FROW;
+        double *ltp = LTp + (size_t)k0 * LROW;
         const int wr = (lane >= 8) ? lane - 8 : 24 + lane;      // window row (after the slide) of the row this lane hands over
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -282,9 +297,8 @@ __device__ __noinline__ bool factor_chain(IpShared &sh, const double *__restrict
             if (!(dj > 0.0)) ok = false;
             const double w = fast_rcp(dj);
             const double lt = p[j] * w, lt2 = p2[j] * w;           // (lanes <= j: lt is not an entry of L; lanes > j: lt2 = 0)
-            // column k0 + j of L: lane l > j holds row k0 + l (offset l - j - 1), lane l <= j the entering row (offset 31 + l - j)
-            __stcs(ltp + j * FROW + ((lane - j - 1) & 31), (lane > j) ? lt : lt2);
             ho.vb[wr * VBP + j] = (lane >= 8) ? lt : lt2;
+            __stcs(ltp + j * LROW + 8 + wr, (lane >= 8) ? lt : lt2);      // L21: the 32 rows below the panel
             if (lane < 8 && lane > j) ho.l11[lane * 8 + j] = lt;
             if (lane == j) { dsave = dj; wsave = w; ysave = yj; }
             gv = fma(-lt, yj, gv);                                 // (lanes <= j: gv is dead)
@@ -300,9 +314,28 @@ __device__ __noinline__ bool factor_chain(IpShared &sh, const double *__restrict
         if (lane < 8) {
             ho.w[lane] = wsave;
             ho.y[lane] = ysave;
-            __stcs(ltp + lane * FROW + 33, wsave);
         }
         __syncwarp();
+        // ---- (2b) Q = L11^-1 (the panel's unit-lower block): with it the panel's triangular solves in the sweeps are mat-vecs.
+        //      LT[k0+j] = [ (Q - I)[0..7][j], L21[0..31][j] (stored above), t, w ] ----
+        {
+            const int jq = lane & 7;
+            double q8[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                double sacc = (m == jq) ? 1.0 : 0.0;
+#pragma unroll
+                for (int i = 0; i < m; ++i) sacc = fma(-ho.l11[m * 8 + i], q8[i], sacc);
+                q8[m] = sacc;
+            }
+            if (lane < 8) {
+                double *ltq = LTp + (size_t)(k0 + lane) * LROW;
+#pragma unroll
+                for (int m = 0; m < 8; m += 2)
+                    __stcs(reinterpret_cast<double2 *>(ltq + m), make_double2((m == lane) ? 0.0 : q8[m], (m + 1 == lane) ? 0.0 : q8[m + 1]));
+                __stcs(ltq + 41, wsave);
+            }
+        }
         // ---- (3) trailing update on the tensor cores; the window slides by one block ----
         double af[4][2], bf[4][2];
 #pragma unroll
@@ -366,15 +399,20 @@ __device__ __noinline__ void factor_fill(IpShared &sh, const double *__restrict_
             gp[j] = uu.x; gp[j + 1] = uu.y;
         }
         const bool hasY = (k0 < 32) || (k0 + SUB - 1 >= NA - 32);     // Y = M[sep, chain] is nonzero across the wrap and next to the separator
+        if (hasY) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = k0 + j;
-            double yv = 0.0;
-            if (hasY && k < NA) {
-                if (k <= lane) yv = HBp[(size_t)(NA + lane) * HB_PITCH + (k + 32 - lane)];
-                else if (k >= NA + lane - 32) yv = HBp[(size_t)k * HB_PITCH + (NA + lane - k)];
+            for (int j = 0; j < 8; ++j) {
+                const int k = k0 + j;
+                double yv = 0.0;
+                if (k < NA) {
+                    if (k <= lane) yv = HBp[(size_t)(NA + lane) * HB_PITCH + (k + 32 - lane)];
+                    else if (k >= NA + lane - 32) yv = HBp[(size_t)k * HB_PITCH + (NA + lane - k)];
+                }
+                gp[j] = yv - gp[j];
             }
-            gp[j] = yv - gp[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gp[j] = -gp[j];
         }
         __syncwarp();
         PROF_T0(tw2);
@@ -537,138 +575,170 @@ __device__ __noinline__ bool factor(IpShared &sh, double *slab, const Layout &L,
 }
 
 // ---- sweep ring: one warp consumes 8-column units streamed HBM -> shared by bulk copies it issues itself ----
-struct Ring {
+template <int SLOTS, int BASE, int UNIT_DOUBLES, int WHO>
+struct RingT {
     IpShared &sh;
+    double *buf;
     unsigned phase;
     uint64_t pol;
-    __device__ Ring(IpShared &s) : sh(s), phase(s.ring_phase), pol(l2_evict_first_policy()) {}
-    __device__ __forceinline__ void issue(int unit, const double *rows) {
-        const int sl = unit % RING_UNITS;
-        mbar_expect_tx(&sh.ring_full[sl], FUNIT_BYTES);
-        tma_load_1d(sh.u.ring[sl], rows + (size_t)unit * SUB * FROW, FUNIT_BYTES, &sh.ring_full[sl], pol);
+    __device__ RingT(IpShared &s, double *b) : sh(s), buf(b), phase(s.ring_phase[WHO]), pol(l2_evict_first_policy()) {}
+    // unit -> slot `sl` (the callers walk the slots cyclically: no modulo on the serial paths)
+    __device__ __forceinline__ void issue(int unit, int sl, const double *rows) {
+        const unsigned bytes = (unsigned)(UNIT_DOUBLES * sizeof(double));
+        mbar_expect_tx(&sh.ring_full[BASE + sl], bytes);
+        tma_load_1d(buf + sl * UNIT_DOUBLES, rows + (size_t)unit * UNIT_DOUBLES, bytes, &sh.ring_full[BASE + sl], pol);
     }
-    __device__ __forceinline__ const double *wait(int unit) {
-        const int sl = unit % RING_UNITS;
+    __device__ __forceinline__ const double *wait(int sl) {
 #ifdef MC_PROFILE
         const long long tw = clock64();
 #endif
-        mbar_wait(&sh.ring_full[sl], (phase >> sl) & 1u);
+        mbar_wait(&sh.ring_full[BASE + sl], (phase >> sl) & 1u);
 #ifdef MC_PROFILE
-        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&g_prof[22 + (threadIdx.x >> 5)], (unsigned long long)(clock64() - tw));
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&g_prof[22 + WHO], (unsigned long long)(clock64() - tw));
 #endif
         phase ^= 1u << sl;
-        return sh.u.ring[sl];
+        return buf + sl * UNIT_DOUBLES;
     }
-    __device__ __forceinline__ void close() { sh.ring_phase = phase; }
+    __device__ __forceinline__ void close() { sh.ring_phase[WHO] = phase; }
 };
+using LtRing = RingT<LT_SLOTS, 0, LT_UNIT_DOUBLES, 0>;
+using GtRing = RingT<GT_SLOTS, LT_SLOTS, GT_UNIT_DOUBLES, 1>;
 
-// forward sweep (warp 0): y = L^-1 g, one panel of eight columns at a time.  lane l = row k0 + l (lanes 0..7 also carry the
-// entering row k0 + 32 + l).  The panel's 8x8 unit-lower solve is done redundantly by every lane from broadcast loads (a
-// chain of dependent DFMAs, no shuffle in it), then each lane updates its own row with eight DFMAs.
-// z = w y goes into the fill rows (GT[k][32]) for the separator's part of the substitution.
+// progress counters between the two warps of a sweep (shared memory, CTA scope)
+__device__ __forceinline__ void prog_publish(int *p, int v) { asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory"); }
+__device__ __forceinline__ int prog_read(const int *p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+// wait until *p >= need (bounded: a protocol error must not hang the device; it is reported like a failed pivot)
+__device__ __forceinline__ void prog_wait(IpShared &sh, const int *p, int need) {
+    for (int spin = 0; spin < (1 << 18); ++spin)
+        if (prog_read(p) >= need) return;
+    sh.flag = 1;
+}
+
+// forward sweep (warp 0): y = L^-1 g, one panel of eight columns at a time, as mat-vecs on the tensor cores.  With the
+// panel stored as [Q - I; L21] (Q = L11^-1, L21 the 32 rows below) the step is
+//   y1 = a1 + (Q - I) a1,   a[k0+8 .. k0+39] -= L21 y1       (rows k0+32 .. k0+39 enter with g).
+// The window a lives in DMMA C fragments (every column of the 8 x 8 tile carries the same vector): lane (gq, q) holds
+// a[k0 + 8 I + gq], I = 0..3; B operands (a1, y1 at index 4 h + q) come by shuffle.
+// z = w y goes to warp 1 (sweep_sep_rhs runs one unit behind) through the queue sw.q, and into the fill rows (GT[k][32])
+// for the backward half of the solve.
 __device__ __noinline__ void sweep_forward(IpShared &sh, const double *__restrict__ HBp, double *__restrict__ LTp, double *__restrict__ GTp, const int NA, const double *__restrict__ g) {
     const int lane = threadIdx.x & 31;
+    const int gq = lane >> 2, q = lane & 3;
     const int nunits = (NA + SUB - 1) / SUB;
-    Ring R(sh);
+    constexpr int AHEAD = LT_SLOTS - 1;
+    LtRing R(sh, &sh.u.sw.lt[0][0]);
     if (lane == 0)
-        for (int u = 0; u < 6 && u < nunits; ++u) R.issue(u, LTp);
-    double acc = (lane < NA) ? g[lane] : 0.0;
+        for (int u = 0; u < AHEAD && u < nunits; ++u) R.issue(u, u, LTp);
+    double acc[4];
+#pragma unroll
+    for (int I = 0; I < 4; ++I) acc[I] = (8 * I + gq < NA) ? g[8 * I + gq] : 0.0;
     double gcur = (32 + lane < NA) ? g[32 + lane] : 0.0;       // g of the rows that enter over the next four panels,
     double gnext = (64 + lane < NA) ? g[64 + lane] : 0.0;      // and the block after it (loaded a block ahead)
-    for (int u = 0; u < nunits; ++u) {
+    int sl = 0, sn = AHEAD % LT_SLOTS;            // slots of unit u and of unit u + AHEAD
+    for (int u = 0; u < nunits; ++u, sl = (sl == LT_SLOTS - 1) ? 0 : sl + 1, sn = (sn == LT_SLOTS - 1) ? 0 : sn + 1) {
         const int k0 = u * SUB;
         if (u > 0 && (u & 3) == 0) {
             gcur = gnext;
             const int idx = k0 + 64 + lane;
             gnext = (idx < NA) ? g[idx] : 0.0;
         }
-        const double *lt = R.wait(u);
-        double acc2 = __shfl_sync(FULL, gcur, ((u & 3) << 3) + (lane & 7));
-        if (lane >= 8) acc2 = 0.0;
-        // this lane's entries of the eight columns: row k0 + l for l > j, the entering row for l <= j
-        double la[8], lb[8];
+        if ((u & 7) == 0 && u >= 8) prog_wait(sh, &sh.prog[1], u - 8);      // queue slots of units u .. u+7 are free again
+        const double *lt = R.wait(sl) + q * LROW + gq;           // A fragments: column 4 h + q of the panel, row (8 I +) gq
+        const double ge = __shfl_sync(FULL, gcur, ((u & 3) << 3) + gq);
+        double a[5][2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const double l = lt[j * FROW + ((lane - j - 1) & 31)];
-            la[j] = (lane > j) ? l : 0.0;
-            lb[j] = (lane > j) ? 0.0 : l;
+        for (int I = 0; I < 5; ++I) {
+            a[I][0] = lt[8 * I];
+            a[I][1] = lt[4 * LROW + 8 * I];
         }
-        const double wl = lt[(lane & 7) * FROW + 33];
-        double l11[28];                            // the panel's unit-lower block L[k0+m][k0+j], m > j: all loads before the chain
+        const double wl = lt[(gq - q) * LROW + 41 - gq];        // w of column k0 + gq
+        // y1 = a1 + (Q - I) a1: two independent products
+        const double b0 = __shfl_sync(FULL, acc[0], 4 * q), b1 = __shfl_sync(FULL, acc[0], 16 + 4 * q);
+        double y0[2] = {acc[0], acc[0]}, y1[2] = {0.0, 0.0};
+        dmma(y0, a[0][0], b0);
+        dmma(y1, a[0][1], b1);
+        const double y = y0[0] + y1[0];
+        const double n0 = -__shfl_sync(FULL, y, 4 * q), n1 = -__shfl_sync(FULL, y, 16 + 4 * q);
+        double nw[4];
 #pragma unroll
-        for (int j = 0; j < 7; ++j)
-#pragma unroll
-            for (int m = j + 1; m < 8; ++m) l11[(m * (m - 1)) / 2 + j] = lt[j * FROW + (m - j - 1)];
-        double y[8];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) y[m] = __shfl_sync(FULL, acc, m);
-#pragma unroll
-        for (int j = 0; j < 7; ++j)                 // right-looking: y[j] is final, the updates of one column are independent
-#pragma unroll
-            for (int m = j + 1; m < 8; ++m) y[m] = fma(-l11[(m * (m - 1)) / 2 + j], y[j], y[m]);
-        {
-            double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;       // two partial sums per row: half the dependent chain
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-                e0 = fma(la[j], y[j], e0); e1 = fma(la[j + 1], y[j + 1], e1);
-                f0 = fma(lb[j], y[j], f0); f1 = fma(lb[j + 1], y[j + 1], f1);
-            }
-            acc -= e0 + e1;                         // (lanes 0..7 end up with their own y)
-            acc2 -= f0 + f1;
+        for (int I = 0; I < 4; ++I) {                  // block 0 (rows k0+8 ..) first: it is the next panel's a1
+            const double c = (I < 3) ? acc[I + 1] : ge;
+            double c0[2] = {c, c}, c1[2] = {0.0, 0.0};
+            dmma(c0, a[I + 1][0], n0);
+            dmma(c1, a[I + 1][1], n1);
+            nw[I] = c0[0] + c1[0];
         }
-        if (lane < 8 && k0 + lane < NA) GTp[(size_t)(k0 + lane) * FROW + 32] = acc * wl;
-        {
-            const double up = __shfl_sync(FULL, acc, (lane + 8) & 31), en = __shfl_sync(FULL, acc2, (lane - 24) & 31);
-            acc = (lane < 24) ? up : en;
+        if (q == 0) {
+            const bool in = (k0 + gq < NA);
+            const double z = in ? y * wl : 0.0;
+            sh.u.sw.q[(u & (QDEPTH - 1)) * SUB + gq] = z;
+            if (in) GTp[(size_t)(k0 + gq) * FROW + 32] = z;
         }
+#pragma unroll
+        for (int I = 0; I < 4; ++I) acc[I] = nw[I];
         __syncwarp();
-        if (lane == 0 && u + 6 < nunits) R.issue(u + 6, LTp);
+        if (lane == 0) {
+            prog_publish(&sh.prog[0], u + 1);
+            if (u + AHEAD < nunits) R.issue(u + AHEAD, sn, LTp);
+        }
     }
     R.close();
     fence_proxy_async();        // z (generic-proxy stores) is read back through bulk copies (async proxy)
 }
 
-// separator part of the forward sweep (warp 1):  gs = g_S - G z
+// separator part of the forward sweep (warp 1, one unit behind warp 0):  gs = g_S - G z
 __device__ __noinline__ void sweep_sep_rhs(IpShared &sh, const double *__restrict__ HBp, double *__restrict__ LTp, double *__restrict__ GTp, const int NA, const double *__restrict__ g) {
     const int lane = threadIdx.x & 31;
     const int nunits = (NA + SUB - 1) / SUB;
-    Ring R(sh);
+    constexpr int AHEAD = GT_SLOTS - 1;
+    GtRing R(sh, &sh.u.sw.gt[0][0]);
     if (lane == 0)
-        for (int u = 0; u < 6 && u < nunits; ++u) R.issue(u, GTp);
+        for (int u = 0; u < AHEAD && u < nunits; ++u) R.issue(u, u, GTp);
     double s0 = 0.0, s1 = 0.0;
     const double gsl = g[NA + lane];
-    for (int u = 0; u < nunits; ++u) {
-        const int nst = min(SUB, NA - u * SUB);
-        const double *gt = R.wait(u);
+    int sl = 0, sn = AHEAD % GT_SLOTS;
+    for (int u = 0; u < nunits; ++u, sl = (sl == GT_SLOTS - 1) ? 0 : sl + 1, sn = (sn == GT_SLOTS - 1) ? 0 : sn + 1) {
+        const double *gt = R.wait(sl) + lane;
+        prog_wait(sh, &sh.prog[0], u + 1);
+        const double *zq = &sh.u.sw.q[(u & (QDEPTH - 1)) * SUB];       // (padding columns: z = 0, g = 0)
 #pragma unroll
-        for (int s = 0; s < SUB; s += 2) {
-            if (s < nst) s0 = fma(gt[s * FROW + lane], gt[s * FROW + 32], s0);
-            if (s + 1 < nst) s1 = fma(gt[(s + 1) * FROW + lane], gt[(s + 1) * FROW + 32], s1);
+        for (int s2 = 0; s2 < SUB; s2 += 2) {
+            s0 = fma(gt[s2 * FROW], zq[s2], s0);
+            s1 = fma(gt[(s2 + 1) * FROW], zq[s2 + 1], s1);
         }
         __syncwarp();
-        if (lane == 0 && u + 6 < nunits) R.issue(u + 6, GTp);
+        if (lane == 0) {
+            prog_publish(&sh.prog[1], u + 1);
+            if (u + AHEAD < nunits) R.issue(u + AHEAD, sn, GTp);
+        }
     }
     R.close();
     sh.gs[lane] = gsl - (s0 + s1);
 }
 
-// separator solve and the right-hand side of the backward sweep (warp 1):
-//   x_S = S^-1 gs;   t = (y - G^T x_S) w = z - w G^T x_S   -> LT[k][32]
+// separator solve and the right-hand side of the backward sweep (warp 1, ahead of warp 0's sweep_backward):
+//   x_S = S^-1 gs;   t = (y - G^T x_S) w = z - w G^T x_S, from the last unit down, handed over through the queue sw.q
 __device__ __noinline__ void sweep_sep_solve(IpShared &sh, const double *__restrict__ HBp, double *__restrict__ LTp, double *__restrict__ GTp, const int NA, double *__restrict__ x) {
     const int lane = threadIdx.x & 31;
     const int nunits = (NA + SUB - 1) / SUB;
-    Ring R(sh);
+    constexpr int AHEAD = GT_SLOTS - 1;
+    GtRing R(sh, &sh.u.sw.gt[0][0]);
+    const int U0 = nunits - 1;
     if (lane == 0)
-        for (int u = 0; u < 6 && u < nunits; ++u) R.issue(u, GTp);
+        for (int i = 0; i < AHEAD && i < nunits; ++i) R.issue(U0 - i, i, GTp);
     double a = sh.gs[lane];
-#pragma unroll
+#pragma unroll 4
     for (int k = 0; k < 32; ++k) {
         const double yk = __shfl_sync(FULL, a, k);
         const double l = (lane > k) ? sh.s.Ss[lane * 33 + k] : 0.0;
         a = fma(-l, yk, a);
     }
     a *= sh.wS[lane];
-#pragma unroll
+#pragma unroll 4
     for (int k = 31; k >= 0; --k) {
         const double xk = __shfl_sync(FULL, a, k);
         const double l = (lane < k) ? sh.s.Ss[k * 33 + lane] : 0.0;
@@ -680,132 +750,108 @@ __device__ __noinline__ void sweep_sep_solve(IpShared &sh, const double *__restr
     double xq[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) xq[i] = __shfl_sync(FULL, a, 8 * qr + i);
-    for (int u = 0; u < nunits; ++u) {
-        const int k = u * SUB + kl;
-        const double *gt = R.wait(u) + kl * FROW;
+    int sl = 0, sn = AHEAD % GT_SLOTS;
+    for (int i = 0; i < nunits; ++i, sl = (sl == GT_SLOTS - 1) ? 0 : sl + 1, sn = (sn == GT_SLOTS - 1) ? 0 : sn + 1) {
+        const int k = (U0 - i) * SUB + kl;
+        if ((i & 7) == 0 && i >= 8) prog_wait(sh, &sh.prog[2], i - 8);      // queue slots of the next eight units are free again
+        const double *gt = R.wait(sl) + kl * FROW;
         const double2 zw = *reinterpret_cast<const double2 *>(&gt[32]);
         double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-            const double2 gg = *reinterpret_cast<const double2 *>(&gt[8 * qr + i]);
-            c0 = fma(gg.x, xq[i], c0);
-            c1 = fma(gg.y, xq[i + 1], c1);
+        for (int e = 0; e < 8; e += 2) {
+            const double2 gg = *reinterpret_cast<const double2 *>(&gt[8 * qr + e]);
+            c0 = fma(gg.x, xq[e], c0);
+            c1 = fma(gg.y, xq[e + 1], c1);
         }
         double c = c0 + c1;
         c += __shfl_xor_sync(FULL, c, 8);
         c += __shfl_xor_sync(FULL, c, 16);
-        if (qr == 0 && k < NA) LTp[(size_t)k * FROW + 32] = fma(-c, zw.y, zw.x);
+        if (qr == 0) sh.u.sw.q[(i & (QDEPTH - 1)) * SUB + kl] = (k < NA) ? fma(-c, zw.y, zw.x) : 0.0;      // (padding rows: t = 0)
         __syncwarp();
-        if (lane == 0 && u + 6 < nunits) R.issue(u + 6, GTp);
+        if (lane == 0) {
+            prog_publish(&sh.prog[3], i + 1);
+            if (i + AHEAD < nunits) R.issue(U0 - i - AHEAD, sn, GTp);
+        }
     }
     R.close();
-    fence_proxy_async();        // t (generic-proxy stores) is read back through bulk copies (async proxy)
 }
 
-// backward sweep (warp 0): x = L^-T t, one panel at a time from the last one.  Before panel k0 lane l holds the
-// accumulator of row k0 - 24 + l (the panel's rows are lanes 24..31), lanes 0..7 also the entering row k0 - 32 + l.
-// The panel's 8x8 unit-upper solve is done redundantly by every lane from broadcast loads; each row then takes the eight
-// entries L[k0+m][row] = LT[row][k0+m-row-1] it needs from its own (resident) factor row: five units resident, two in flight.
+// backward sweep (warp 0): x = L^-T t, one panel at a time from the last one, as mat-vecs on the tensor cores:
+//   u = t1 - L21^T x[k0+8 .. k0+39],   x[k0 .. k0+7] = u + (Q - I)^T u.
+// The 32 x's below the panel are kept NEGATED as B operands (lane (gq, q): -x[k0 + 8 + 4 i + q], i = 0..7); u and the eight new
+// x's come out in C layout (lane (gq, .): row k0 + gq) and move over by shuffle.  Only the two products with the previous
+// panel's x and the two with u are on the chain from panel to panel; the other six are issued ahead of them.
+// t comes from warp 1 (sweep_sep_solve, running ahead) through the queue sw.q.
 __device__ __noinline__ void sweep_backward(IpShared &sh, const double *__restrict__ HBp, double *__restrict__ LTp, double *__restrict__ GTp, const int NA, double *__restrict__ x) {
     const int lane = threadIdx.x & 31;
+    const int gq = lane >> 2, q = lane & 3;
     const int nunits = (NA + SUB - 1) / SUB;
-    SEG_BEGIN();
-    Ring R(sh);
+    constexpr int AHEAD = LT_SLOTS - 1;
+    LtRing R(sh, &sh.u.sw.lt[0][0]);
     const int U0 = nunits - 1;
-    SEG(16);
     if (lane == 0)
-        for (int u = U0; u > U0 - 6 && u >= 0; --u) R.issue(u, LTp);
-    SEG(17);
-    for (int u = U0; u > U0 - 4 && u >= 0; --u) R.wait(u);            // rows k0 - 24 .. k0 + 7 of the first panel
-    SEG(18);
-    double acc;
-    {
-        const int r1 = U0 * SUB - 24 + lane;
-        acc = (r1 >= 0 && r1 < NA) ? sh.u.ring[(r1 >> 3) % RING_UNITS][(r1 & 7) * FROW + 32] : 0.0;     // t of the row
-    }
-    SEG(19);
-    for (int U = U0; U >= 0; --U) {
-        const int k0 = U * SUB;
-        SEG(0);
-        if (U - 4 >= 0) R.wait(U - 4);
-        SEG(1);
-        const double *ltU = sh.u.ring[U % RING_UNITS];
-        const int r1 = k0 - 24 + lane, r2 = k0 - 32 + lane;
-        // rows of this lane: r1 in unit U - 3 + (lane >> 3), r2 (lanes 0..7) in unit U - 4, both at row lane & 7 of their unit
-        const double *p1 = &sh.u.ring[(U + 4 + (lane >> 3)) % RING_UNITS][(lane & 7) * FROW];
-        const double *p2 = &sh.u.ring[(U + 3) % RING_UNITS][(lane & 7) * FROW];
-        double l1[8], l2[8];
+        for (int i = 0; i < AHEAD && i < nunits; ++i) R.issue(U0 - i, i, LTp);
+    double nbx[8];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int o1 = 23 - lane + m, o2 = 31 - lane + m;          // k0 + m - row - 1
-            l1[m] = (r1 >= 0 && o1 >= 0) ? p1[o1] : 0.0;
-            l2[m] = (lane < 8 && r2 >= 0 && o2 <= 31) ? p2[o2] : 0.0;
+    for (int i = 0; i < 8; ++i) nbx[i] = 0.0;
+    int sl = 0, sn = AHEAD % LT_SLOTS;
+    for (int i = 0; i < nunits; ++i, sl = (sl == LT_SLOTS - 1) ? 0 : sl + 1, sn = (sn == LT_SLOTS - 1) ? 0 : sn + 1) {
+        const int k0 = (U0 - i) * SUB;
+        const double *lt = R.wait(sl) + gq * LROW + q;           // A fragments: column gq of the panel, row 4 c + q
+        double a[10];
+#pragma unroll
+        for (int c = 0; c < 10; ++c) a[c] = lt[4 * c];
+        double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+#pragma unroll
+        for (int e = 2; e < 8; e += 2) {
+            dmma(c0, a[2 + e], nbx[e]);
+            dmma(c1, a[3 + e], nbx[e + 1]);
         }
-        double acc2 = (lane < 8 && r2 >= 0) ? p2[32] : 0.0;            // t of the entering row
-        double l11[28];                            // L[k0+mm][k0+m], mm > m: all loads before the chain
+        dmma(c0, a[2], nbx[0]);
+        dmma(c1, a[3], nbx[1]);
+        prog_wait(sh, &sh.prog[3], i + 1);
+        const double t1 = sh.u.sw.q[(i & (QDEPTH - 1)) * SUB + gq];
+        const double uu = t1 + (c0[0] + c1[0]);
+        const double u0 = __shfl_sync(FULL, uu, 4 * q), u1 = __shfl_sync(FULL, uu, 16 + 4 * q);
+        double d0[2] = {uu, uu}, d1[2] = {0.0, 0.0};
+        dmma(d0, a[0], u0);
+        dmma(d1, a[1], u1);
+        const double x1 = d0[0] + d1[0];
+        if (q == 0 && k0 + gq < NA) x[k0 + gq] = x1;
 #pragma unroll
-        for (int m = 0; m < 7; ++m)
-#pragma unroll
-            for (int mm = m + 1; mm < 8; ++mm) l11[(mm * (mm - 1)) / 2 + m] = ltU[m * FROW + (mm - m - 1)];
-        SEG(2);
-        double xv[8];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) xv[m] = __shfl_sync(FULL, acc, 24 + m);
-        SEG(3);
-#pragma unroll
-        for (int mm = 7; mm >= 1; --mm)            // right-looking: xv[mm] is final, the updates of one column are independent
-#pragma unroll
-            for (int m = 0; m < mm; ++m) xv[m] = fma(-l11[(mm * (mm - 1)) / 2 + m], xv[mm], xv[m]);
-        {
-            double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
-#pragma unroll
-            for (int m = 0; m < 8; m += 2) {
-                e0 = fma(l1[m], xv[m], e0); e1 = fma(l1[m + 1], xv[m + 1], e1);
-                f0 = fma(l2[m], xv[m], f0); f1 = fma(l2[m + 1], xv[m + 1], f1);
-            }
-            acc -= e0 + e1;                         // (lanes 24..31 end up with their own x)
-            acc2 -= f0 + f1;
-        }
-        SEG(4);
-        if (lane >= 24 && r1 < NA) x[r1] = acc;
-        {
-            const double dn = __shfl_sync(FULL, acc, (lane - 8) & 31);
-            acc = (lane >= 8) ? dn : acc2;
-        }
+        for (int e = 7; e >= 2; --e) nbx[e] = nbx[e - 2];
+        nbx[0] = -__shfl_sync(FULL, x1, 4 * q);
+        nbx[1] = -__shfl_sync(FULL, x1, 16 + 4 * q);
         __syncwarp();
-        SEG(5);
-        if (lane == 0 && U - 6 >= 0) R.issue(U - 6, LTp);            // slot of unit U + 1
-        SEG(6);
+        if (lane == 0) {
+            prog_publish(&sh.prog[2], i + 1);
+            if (i + AHEAD < nunits) R.issue(U0 - i - AHEAD, sn, LTp);
+        }
     }
-    SEG(20);
     R.close();
-    SEG(21);
 }
 
-// x = M^-1 g with the stored factor.  fused: the forward part was done inside factor() (predictor).
+// x = M^-1 g with the stored factor.  fused: the forward part was done inside factor() (predictor).  Both halves run on the
+// two warps concurrently: warp 1's separator reduction trails warp 0's forward sweep, then (after the separator solve)
+// warp 1's right-hand side t runs ahead of warp 0's backward sweep.
 __device__ __noinline__ void solve(IpShared &sh, double *slab, const Layout &L, int n, const double *g, double *x, bool fused) {
     const Factor F = make_factor(slab, L, n);
     const int warp = threadIdx.x >> 5;
+    if (threadIdx.x < 4) sh.prog[threadIdx.x] = 0;
     fence_proxy_async();        // the ring area was last accessed through the generic proxy (factor hand-off buffers)
     __syncthreads();
     if (!fused) {
         PROF_T0(t0);
         if (warp == 0) sweep_forward(sh, F.HB, F.LT, F.GT, F.NA, g);
+        else sweep_sep_rhs(sh, F.HB, F.LT, F.GT, F.NA, g);
         __syncthreads();
-        PROF_ADD(2, t0);
-        PROF_T0(t1);
-        if (warp == 1) sweep_sep_rhs(sh, F.HB, F.LT, F.GT, F.NA, g);
-        __syncwarp();
-        PROF_ADD1(3, t1);
+        PROF_ADD1(2, t0);
     }
-    PROF_T0(t2);
-    if (warp == 1) sweep_sep_solve(sh, F.HB, F.LT, F.GT, F.NA, x);
-    PROF_ADD1(4, t2);
-    __syncthreads();
     PROF_T0(t3);
-    if (warp == 0) sweep_backward(sh, F.HB, F.LT, F.GT, F.NA, x);
+    if (warp == 1) sweep_sep_solve(sh, F.HB, F.LT, F.GT, F.NA, x);
+    else sweep_backward(sh, F.HB, F.LT, F.GT, F.NA, x);
     __syncthreads();
-    PROF_ADD(8, t3);
+    PROF_ADD1(8, t3);
 }
 
 // banded cyclic mat-vec out = H v (real-indexed)
@@ -832,7 +878,7 @@ __device__ __forceinline__ void ip_init_shared(IpShared &sh) {
         for (int i = 0; i < HB_SLOTS; ++i) mbar_init(&sh.hb_full[i], 1);
         for (int i = 0; i < HO_SLOTS; ++i) { mbar_init(&sh.ho_full[i], 1); mbar_init(&sh.ho_empty[i], 1); }
         for (int i = 0; i < RING_UNITS; ++i) mbar_init(&sh.ring_full[i], 1);
-        sh.ring_phase = 0;
+        sh.ring_phase[0] = 0; sh.ring_phase[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -844,6 +890,13 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
                     int32_t *__restrict__ iters_out, int *__restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     IpShared &sh = *reinterpret_cast<IpShared *>(smem_raw);
+#ifdef MC_DEBUG_SM_LIMIT       // contention experiments: only the first MC_DEBUG_SM_LIMIT SMs take work (full occupancy on those)
+    {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (smid >= MC_DEBUG_SM_LIMIT) return;
+    }
+#endif
     ip_init_shared(sh);
     unsigned tick = 0;      // hand-off units of the factorisations so far (uniform across the CTA)
 

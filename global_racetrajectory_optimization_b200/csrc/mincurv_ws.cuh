@@ -41,7 +41,7 @@ __host__ __device__ inline Layout make_layout(int n_max) {
     L.o_hb = o;
     o += (size_t)L.np * HB_PITCH;
     L.o_tiles = o;
-    o += (size_t)L.np * 68;
+    o += (size_t)L.np * 76;
     L.stride = (o + 15) & ~(size_t)15;
     return L;
 }

@@ -83,6 +83,9 @@ def test_every_wrapper_matches_the_signature_table(fake):
     assert B_.check_normals_crossing_batch(rt, nv, 10, n_pts=npts).shape == (B,)
     with pytest.raises(RuntimeError, match="too large"):
         B_.check_normals_crossing_batch(rt, nv, n, n_pts=npts)
+    raw = torch.rand((B, 300, 4), dtype=torch.float64) + 3.0
+    smoothed, n_smoothed, lam = B_.spline_approximation_batch(raw, k_reg=3, s_reg=10.0, stepsize_prep=1.0, stepsize_reg=3.0)
+    assert smoothed.shape[0] == B and smoothed.shape[2] == 4 and n_smoothed.shape == (B,) and lam.shape == (B,)
     used = set(_names(fake))
     assert used >= set(_lib.EXPORTED_SYMBOLS) - {"mc_version", "mc_last_error", "mc_debug_read_profile", "mc_debug_factor_solve",
                                                  "mc_mincurv_setup_batch", "mc_mincurv_setup_batch_ex", "mc_mincurv_solve_batch",
