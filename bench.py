@@ -182,6 +182,10 @@ def build_workload(cfg_name, args, dev, rank, torch, B_, lib, _lib):
 
     if cfg_name == "c1":
         ws = B_._workspace("mincurv", lib.mc_mincurv_workspace_bytes(bl, n), dev)
+        # variant i is a width jitter of centre line i % N_BASE_LINES (make_inputs): H, f and k_ref depend on the centre line
+        # only and are assembled once per centre line (centre_id of mc_mincurv_setup_batch_shared)
+        W["centre_id"] = (torch.arange(bl, device=dev) % min(N_BASE_LINES, bl)).to(torch.int32)
+        W["facts"]["shared_centre_lines"] = f"{min(N_BASE_LINES, bl)} centre lines for {bl} instances: QP matrices assembled once per centre line"
 
         def step(rt_dev, tm):
             with tm.span("splines"):
@@ -194,7 +198,8 @@ def build_workload(cfg_name, args, dev, rank, torch, B_, lib, _lib):
             iters = torch.empty((Bq,), dtype=torch.int32, device=dev)
             s = s_()
             with tm.span("setup"):
-                _lib.check(lib.mc_mincurv_setup_batch(Bq, n, None, p(rt_dev), p(nv), p(h), W_VEH, None, p(st), p(ws), ws.numel(), s), "setup")
+                _lib.check(lib.mc_mincurv_setup_batch_shared(Bq, n, None, p(rt_dev), p(nv), p(h), W_VEH, None, B_.F_SCALE,
+                                                             p(W["centre_id"]), p(st), p(ws), ws.numel(), s), "setup")
             with tm.span("pdip"):
                 _lib.check(lib.mc_mincurv_pdip_batch(Bq, n, None, p(alpha), p(st), p(iters), p(ws), ws.numel(), s), "pdip")
             _lib.check(lib.mc_mincurv_finalize_batch(Bq, n, None, p(alpha), KAPPA_BOUND, p(cerr), p(kmax), p(st), p(ws), ws.numel(), s), "finalize")
@@ -237,7 +242,8 @@ def build_workload(cfg_name, args, dev, rank, torch, B_, lib, _lib):
                 with tm.span("splines"):
                     cx, cy, nv, h = B_.calc_splines_batch(rt_dev, want_coeffs=False)
                 with tm.span("solve"):
-                    res = B_.opt_min_curv_batch(rt_dev, nv, h, KAPPA_BOUND, W["w_veh"][lo:hi], max_chunk=hi - lo)
+                    cid = B_.shared_centre_ids(torch.arange(hi - lo, device=dev) % W["base"].shape[0])
+                    res = B_.opt_min_curv_batch(rt_dev, nv, h, KAPPA_BOUND, W["w_veh"][lo:hi], max_chunk=hi - lo, centre_id=cid)
                 alpha[lo:hi], status[lo:hi], iters[lo:hi] = res["alpha"], res["status"], res["iters"]
             return dict(alpha=alpha, status=status, iters=iters)
         W.update(step=step, qps_per_step=bl, launches=None)
@@ -249,7 +255,8 @@ def build_workload(cfg_name, args, dev, rank, torch, B_, lib, _lib):
             with torch.cuda.stream(W["side"]):                       # mincurv on the second stream
                 rt_mc, _ = B_.jitter_widths_batch(W["base"], W["seeds_mc"])
                 cx, cy, nv_mc, h_mc = B_.calc_splines_batch(rt_mc, want_coeffs=False)
-                mc = B_.opt_min_curv_batch(rt_mc, nv_mc, h_mc, KAPPA_BOUND, W_VEH)
+                mc = B_.opt_min_curv_batch(rt_mc, nv_mc, h_mc, KAPPA_BOUND, W_VEH,
+                                           centre_id=B_.shared_centre_ids(torch.arange(4096, device=dev) % W["base"].shape[0]))
             with tm.span("jitter"):
                 rt_sp, _ = B_.jitter_widths_batch(W["base"], W["seeds"])
             with tm.span("splines"):
@@ -456,6 +463,19 @@ def streaming_kernel_times(torch, B_, lib, _lib, rt, alpha, n, n_out_max, dev, r
     return out[0], out[1]
 
 
+def pcie_probe(torch, dev) -> dict:
+    """Pinned-memory copy bandwidth of this box (256 MB each way, one warm-up): what the e2e figure's copies run at."""
+    h = torch.empty(32 * 1024 * 1024, dtype=torch.float64).pin_memory()
+    d = torch.empty(h.shape, dtype=torch.float64, device=dev)
+    out = {}
+    for _ in range(2):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record(); d.copy_(h, non_blocking=True); ev[1].record(); h.copy_(d, non_blocking=True); ev[2].record()
+        torch.cuda.synchronize(dev)
+        out = {"h2d_gbs": h.numel() * 8 / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9, "d2h_gbs": h.numel() * 8 / (ev[1].elapsed_time(ev[2]) * 1e-3) / 1e9}
+    return out
+
+
 def run_e2e(args, W, torch, B_, dev, world, sync_all, dist) -> dict:
     n, bl, cfg = W["n"], W["batch"], W["cfg"]
     n_out_max = W["n_out_max"]
@@ -518,7 +538,7 @@ def run_e2e(args, W, torch, B_, dev, world, sync_all, dist) -> dict:
         cur.wait_event(ev_in[k % 2])
         rt_dev = rt_buf[k % 2]
         cx, cy, nv, h = B_.calc_splines_batch(rt_dev, want_coeffs=False)
-        qp = B_.opt_min_curv_batch(rt_dev, nv, h, KAPPA_BOUND, W_VEH)
+        qp = B_.opt_min_curv_batch(rt_dev, nv, h, KAPPA_BOUND, W_VEH, centre_id=W["centre_id"])
         rl = B_.create_raceline_batch(rt_dev, nv, qp["alpha"], STEP_INTERP, n_out_max=n_out_max, with_head_curv=True)
         ev_free[k % 2].record(cur)
         d2h.wait_stream(cur)
@@ -552,7 +572,8 @@ def run_e2e(args, W, torch, B_, dev, world, sync_all, dist) -> dict:
             "h2d_bytes_per_step": int(host_in.numel() * 8), "d2h_bytes_per_step": d2h_bytes,
             "api": "batch.calc_splines_batch -> batch.opt_min_curv_batch -> batch.create_raceline_batch; results copied to "
                    "pinned host memory: alpha, kappa, raceline x/y, n_out, status",
-            "copies": "H2D and D2H on their own streams, double-buffered", "all_racelines_fit": n_out_ok}
+            "copies": "H2D and D2H on their own streams, double-buffered", "all_racelines_fit": n_out_ok,
+            "pinned_copy_bandwidth": pcie_probe(torch, dev)}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -24,6 +24,9 @@ _SIGS = {
                                         _vp, _sz, _vp]),
     "mc_mincurv_solve_batch_ex": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _c_dbl, _c_dbl, _vp, _c_dbl, _vp, _vp, _vp, _vp,
                                            _vp, _vp, _sz, _vp]),
+    "mc_mincurv_solve_batch_shared": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _c_dbl, _c_dbl, _vp, _c_dbl, _vp, _vp, _vp,
+                                               _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mc_mincurv_setup_batch_shared": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _c_dbl, _vp, _c_dbl, _vp, _vp, _vp, _sz, _vp]),
     "mc_mincurv_setup_batch_ex": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _c_dbl, _vp, _c_dbl, _vp, _vp, _sz, _vp]),
     "mc_mincurv_setup_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _c_dbl, _vp, _vp, _vp, _sz, _vp]),
     "mc_mincurv_pdip_batch": (_c_int, [_c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

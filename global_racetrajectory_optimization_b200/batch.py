@@ -167,10 +167,15 @@ def _chunk(B: int, per_item_bytes: int, device) -> int:
 @_device_guard
 def opt_min_curv_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, kappa_bound: float,
                        w_veh: Union[float, torch.Tensor], n_pts: Optional[torch.Tensor] = None,
-                       max_chunk: Optional[int] = None, f_scale: Optional[float] = None) -> dict:
+                       max_chunk: Optional[int] = None, f_scale: Optional[float] = None,
+                       centre_id: Optional[torch.Tensor] = None) -> dict:
     """Batched tph.opt_min_curv (closed tracks).  Returns a dict of device tensors:
     alpha [B, n_max], curv_error_max [B], kappa_lin_max [B], status [B] (int32), iters [B] (int32).
-    f_scale: None = the module default F_SCALE (see there)."""
+    f_scale: None = the module default F_SCALE (see there).
+    centre_id [B] (optional): for batches in which several instances share a centreline (x, y, normvec, h, n_pts identical;
+    only the widths differ -- a width sweep of one track): centre_id[b] = index of the instance that owns b's centreline
+    (owners: centre_id[b] == b).  H, f and k_ref are then assembled once per centreline (same results, less work);
+    shared_centre_ids() builds the tensor from group labels."""
     _require_cuda()
     lib = _lib.load()
     reftrack = _f64(reftrack, "reftrack")
@@ -192,16 +197,34 @@ def opt_min_curv_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.T
     per_item = lib.mc_mincurv_workspace_bytes(1, n_max)
     chunk = _chunk(B, per_item, dev) if max_chunk is None else min(B, max_chunk)
     ws = _workspace("mincurv", lib.mc_mincurv_workspace_bytes(chunk, n_max), dev)
+    if centre_id is not None:
+        if centre_id.shape != (B,):
+            raise ValueError("centre_id must be [B]")
+        centre_id = centre_id.to(device=dev, dtype=torch.int32).contiguous()
     for s in range(0, B, chunk):
         e = min(B, s + chunk)
-        rc = lib.mc_mincurv_solve_batch_ex(e - s, n_max, _ptr(n_pts[s:e]) if n_pts is not None else None,
-                                           _ptr(reftrack[s:e]), _ptr(normvec[s:e]), _ptr(h[s:e]), float(kappa_bound),
-                                           w_scalar, _ptr(w_batch[s:e]) if w_batch is not None else None,
-                                           float(F_SCALE if f_scale is None else f_scale),
-                                           _ptr(alpha[s:e]), _ptr(cerr[s:e]), _ptr(kmax[s:e]), _ptr(status[s:e]),
-                                           _ptr(iters[s:e]), _ptr(ws), ws.numel(), _stream())
-        _lib.check(rc, "mc_mincurv_solve_batch_ex")
+        cid = None
+        if centre_id is not None:
+            # owners are addressed inside the chunk: the first instance of the chunk with the same owner takes the role
+            cid = centre_id if (s == 0 and e == B) else shared_centre_ids(centre_id[s:e])
+        rc = lib.mc_mincurv_solve_batch_shared(e - s, n_max, _ptr(n_pts[s:e]) if n_pts is not None else None,
+                                               _ptr(reftrack[s:e]), _ptr(normvec[s:e]), _ptr(h[s:e]), float(kappa_bound),
+                                               w_scalar, _ptr(w_batch[s:e]) if w_batch is not None else None,
+                                               float(F_SCALE if f_scale is None else f_scale), _ptr(cid),
+                                               _ptr(alpha[s:e]), _ptr(cerr[s:e]), _ptr(kmax[s:e]), _ptr(status[s:e]),
+                                               _ptr(iters[s:e]), _ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, "mc_mincurv_solve_batch_shared")
     return dict(alpha=alpha, curv_error_max=cerr, kappa_lin_max=kmax, status=status, iters=iters)
+
+
+def shared_centre_ids(group: torch.Tensor) -> torch.Tensor:
+    """centre_id for opt_min_curv_batch from group labels [B] (any integers: instances with equal labels share a
+    centreline): the first instance of every group becomes its owner.  Returns int32 [B] on the labels' device."""
+    vals, inv = torch.unique(group, return_inverse=True)
+    idx = torch.arange(group.shape[0], device=group.device, dtype=torch.int64)
+    first = torch.full((vals.shape[0],), group.shape[0], device=group.device, dtype=torch.int64)
+    first = first.scatter_reduce(0, inv, idx, reduce="amin")
+    return first[inv].to(torch.int32)
 
 
 @_device_guard

@@ -15,7 +15,7 @@ int pdip_kappa_ctas_per_sm();
 int launch_debug_factor_solve(int, int, const int32_t *, double *, const Layout &, int32_t *, cudaStream_t);
 int debug_read_profile(unsigned long long *, int);
 void launch_mincurv_setup(int, int, const int32_t *, const double *, const double *, const double *, double,
-                          const double *, double, double *, const Layout &, int32_t *, cudaStream_t);
+                          const double *, double, const int32_t *, double *, const Layout &, int32_t *, cudaStream_t);
 int launch_mincurv_pdip(int, int, const int32_t *, double *, const Layout &, const PdipParams &, double *, int32_t *,
                         int32_t *, int, int *, cudaStream_t);
 int launch_mincurv_pdip_kappa(int, int, const int32_t *, double *, const Layout &, const PdipParams &, double, double *,
@@ -83,6 +83,9 @@ static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 extern "C" {
 
 int mc_mincurv_kappa_batch(int, int, const int32_t *, double, double *, int32_t *, int32_t *, void *, size_t, void *);
+int mc_mincurv_solve_batch_shared(int, int, const int32_t *, const double *, const double *, const double *, double, double,
+                                  const double *, double, const int32_t *, double *, double *, double *, int32_t *, int32_t *, void *, size_t,
+                                  void *);
 int mc_mincurv_solve_batch_ex(int, int, const int32_t *, const double *, const double *, const double *, double, double,
                               const double *, double, double *, double *, double *, int32_t *, int32_t *, void *, size_t, void *);
 int mc_vel_profile_batch_ex(int, int, const int32_t *, const double *, const double *, const double *, int, const double *,
@@ -130,16 +133,24 @@ static int mincurv_args(const char *who, int B, int n_max, void *workspace, size
     return MC_OK;
 }
 
-int mc_mincurv_setup_batch_ex(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
-                              const double *h, double w_veh, const double *w_veh_batch, double f_scale, int32_t *status,
-                              void *workspace, size_t workspace_bytes, void *stream) {
+int mc_mincurv_setup_batch_shared(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
+                                  const double *h, double w_veh, const double *w_veh_batch, double f_scale,
+                                  const int32_t *centre_id, int32_t *status, void *workspace, size_t workspace_bytes,
+                                  void *stream) {
     if (!reftrack || !normvec || !h || !status) return bad("mc_mincurv_setup_batch: NULL argument");
     if (!(f_scale > 0.0)) return bad("mc_mincurv_setup_batch: f_scale must be positive");
     int rc = mincurv_args("mc_mincurv_setup_batch", B, n_max, workspace, workspace_bytes);
     if (rc) return rc;
-    mc::launch_mincurv_setup(B, n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, f_scale, (double *)workspace,
+    mc::launch_mincurv_setup(B, n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, f_scale, centre_id, (double *)workspace,
                              mc::make_layout(n_max), status, (cudaStream_t)stream);
     return check_cuda("mincurv_setup_kernel");
+}
+
+int mc_mincurv_setup_batch_ex(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
+                              const double *h, double w_veh, const double *w_veh_batch, double f_scale, int32_t *status,
+                              void *workspace, size_t workspace_bytes, void *stream) {
+    return mc_mincurv_setup_batch_shared(B, n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, f_scale, nullptr, status,
+                                         workspace, workspace_bytes, stream);
 }
 
 int mc_mincurv_setup_batch(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
@@ -204,10 +215,18 @@ int mc_mincurv_solve_batch_ex(int B, int n_max, const int32_t *n_pts, const doub
                               const double *h, double kappa_bound, double w_veh, const double *w_veh_batch, double f_scale,
                               double *alpha, double *curv_error_max, double *kappa_lin_max, int32_t *status, int32_t *iters,
                               void *workspace, size_t workspace_bytes, void *stream) {
+    return mc_mincurv_solve_batch_shared(B, n_max, n_pts, reftrack, normvec, h, kappa_bound, w_veh, w_veh_batch, f_scale, nullptr,
+                                         alpha, curv_error_max, kappa_lin_max, status, iters, workspace, workspace_bytes, stream);
+}
+
+int mc_mincurv_solve_batch_shared(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
+                                  const double *h, double kappa_bound, double w_veh, const double *w_veh_batch, double f_scale,
+                                  const int32_t *centre_id, double *alpha, double *curv_error_max, double *kappa_lin_max,
+                                  int32_t *status, int32_t *iters, void *workspace, size_t workspace_bytes, void *stream) {
     if (!reftrack || !normvec || !h || !alpha || !curv_error_max || !status)
         return bad("mc_mincurv_solve_batch: NULL argument");
-    int rc = mc_mincurv_setup_batch_ex(B, n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, f_scale, status, workspace,
-                                       workspace_bytes, stream);
+    int rc = mc_mincurv_setup_batch_shared(B, n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, f_scale, centre_id, status,
+                                           workspace, workspace_bytes, stream);
     if (rc) return rc;
     rc = mc_mincurv_pdip_batch(B, n_max, n_pts, alpha, status, iters, workspace, workspace_bytes, stream);
     if (rc) return rc;

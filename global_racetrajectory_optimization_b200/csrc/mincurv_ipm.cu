@@ -91,16 +91,30 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, unsigned parity
         asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (ok) break;
+#ifndef MC_EXP_SPIN
         __nanosleep(20);
+#endif
     }
 #endif
 }
 // The factor is a stream (written once, read three times per iteration, 0.5 MB per instance, far beyond what L2 can
 // keep for 1184 resident instances): its copies and stores carry an evict-first L2 policy so that they do not push the
 // O(N) iterate vectors of the interior-point loop out of L2.
+template <typename T>
+__device__ __forceinline__ void st_stream(T *p, T v) {
+#ifdef MC_EXP_NOSTCS
+    *p = v;
+#else
+    __stcs(p, v);
+#endif
+}
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     uint64_t pol;
+#ifdef MC_EXP_EVICT_NORMAL
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+#else
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#endif
     return pol;
 }
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar, uint64_t policy) {
@@ -171,7 +185,7 @@ struct IpShared {
     } u;
     union {
         double Ss[32 * 33];                           // separator block -> its L_S (strictly lower, in place)
-        double sfrag[20 * 32];                        // during the chain: S accumulators (DMMA C fragments, lane-major)
+        double sfrag[20 * 32];                        // during the chain: S accumulators (DMMA C fragments, [block][lane][2])
     } s;
     double wS[32], gs[32], part[2][32];
     double red[32];
@@ -298,7 +312,7 @@ __device__ __noinline__ bool factor_chain(IpShared &sh, const double *__restrict
             const double w = fast_rcp(dj);
             const double lt = p[j] * w, lt2 = p2[j] * w;           // (lanes <= j: lt is not an entry of L; lanes > j: lt2 = 0)
             ho.vb[wr * VBP + j] = (lane >= 8) ? lt : lt2;
-            __stcs(ltp + j * LROW + 8 + wr, (lane >= 8) ? lt : lt2);      // L21: the 32 rows below the panel
+            st_stream(ltp + j * LROW + 8 + wr, (lane >= 8) ? lt : lt2);      // L21: the 32 rows below the panel
             if (lane < 8 && lane > j) ho.l11[lane * 8 + j] = lt;
             if (lane == j) { dsave = dj; wsave = w; ysave = yj; }
             gv = fma(-lt, yj, gv);                                 // (lanes <= j: gv is dead)
@@ -332,8 +346,8 @@ __device__ __noinline__ bool factor_chain(IpShared &sh, const double *__restrict
                 double *ltq = LTp + (size_t)(k0 + lane) * LROW;
 #pragma unroll
                 for (int m = 0; m < 8; m += 2)
-                    __stcs(reinterpret_cast<double2 *>(ltq + m), make_double2((m == lane) ? 0.0 : q8[m], (m + 1 == lane) ? 0.0 : q8[m + 1]));
-                __stcs(ltq + 41, wsave);
+                    st_stream(reinterpret_cast<double2 *>(ltq + m), make_double2((m == lane) ? 0.0 : q8[m], (m + 1 == lane) ? 0.0 : q8[m + 1]));
+                st_stream(ltq + 41, wsave);
             }
         }
         // ---- (3) trailing update on the tensor cores; the window slides by one block ----
@@ -427,7 +441,7 @@ __device__ __noinline__ void factor_fill(IpShared &sh, const double *__restrict_
         double *gtp = GTp + (size_t)k0 * FROW;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            __stcs(gtp + j * FROW + lane, gp[j]);
+            st_stream(gtp + j * FROW + lane, gp[j]);
             gsacc = fma(gp[j], ho.w[j] * ho.y[j], gsacc);
         }
         if (lane < 8) {
@@ -465,8 +479,8 @@ __device__ __noinline__ void factor_fill(IpShared &sh, const double *__restrict_
             double c2[4][2];
 #pragma unroll
             for (int J = 0; J <= I; ++J) {
-                c2[J][0] = sh.s.sfrag[(2 * blk(I, J)) * 32 + lane];
-                c2[J][1] = sh.s.sfrag[(2 * blk(I, J) + 1) * 32 + lane];
+                const double2 cc = *reinterpret_cast<const double2 *>(&sh.s.sfrag[(blk(I, J) * 32 + lane) * 2]);
+                c2[J][0] = cc.x; c2[J][1] = cc.y;
             }
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
@@ -475,10 +489,8 @@ __device__ __noinline__ void factor_fill(IpShared &sh, const double *__restrict_
                 for (int J = 0; J <= I; ++J) dmma(c2[J], a, af[J][ks]);
             }
 #pragma unroll
-            for (int J = 0; J <= I; ++J) {
-                sh.s.sfrag[(2 * blk(I, J)) * 32 + lane] = c2[J][0];
-                sh.s.sfrag[(2 * blk(I, J) + 1) * 32 + lane] = c2[J][1];
-            }
+            for (int J = 0; J <= I; ++J)
+                *reinterpret_cast<double2 *>(&sh.s.sfrag[(blk(I, J) * 32 + lane) * 2]) = make_double2(c2[J][0], c2[J][1]);
         }
         __syncwarp();
         PROF_ADD1(21, tw3);
@@ -514,7 +526,7 @@ __device__ __noinline__ bool factor(IpShared &sh, double *slab, const Layout &L,
     double sf[20];
     if (warp == 1) {
 #pragma unroll
-        for (int e = 0; e < 20; ++e) sf[e] = sh.s.sfrag[e * 32 + lane];
+        for (int e = 0; e < 20; ++e) sf[e] = sh.s.sfrag[((e >> 1) * 32 + lane) * 2 + (e & 1)];
     }
     // (the separator block of M: 16 entries per thread, all loads in flight before the barrier)
     double sv[16];

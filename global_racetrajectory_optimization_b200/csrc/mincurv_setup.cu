@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256)
 mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
                      const double *__restrict__ reftrack, const double *__restrict__ normvec,
                      const double *__restrict__ hin, double w_veh, const double *__restrict__ w_veh_batch, double f_scale,
-                     double *__restrict__ ws, Layout L, int32_t *__restrict__ status) {
+                     const int32_t *__restrict__ centre_id, double *__restrict__ ws, Layout L, int32_t *__restrict__ status) {
     const int b = blockIdx.x;
     const int n = n_pts ? n_pts[b] : n_max;
     double *slab = ws + (size_t)b * L.stride;
@@ -70,9 +70,14 @@ mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
         LB[i] = lb; UB[i] = ub;
     }
     __syncthreads();
-    if (s_flag) {
-        if (threadIdx.x == 0) status[b] = 1;
-        return;
+    // Instances that share a centreline (same x, y, normals, spacing: e.g. the width variants of one track) share H, f and
+    // k_ref, only the bounds differ: with centre_id the assembly runs once per centreline (the owner, centre_id[b] == b) and
+    // mincurv_share_kernel copies its result into the followers' slabs.  An owner finishes the assembly even when its own
+    // bounds are infeasible (its followers need it).
+    const bool follower = centre_id && centre_id[b] != b;
+    if (s_flag || follower) {
+        if (threadIdx.x == 0) status[b] = s_flag ? 1 : 0;
+        if (follower || !centre_id) return;
     }
     // ---- P2/P3: periodic LDL^T of the spline system, decay ratios of its inverse ----
     tri_pivots(DG, H, DFW, DBW, n);
@@ -120,16 +125,45 @@ mincurv_setup_kernel(int n_max, const int32_t *__restrict__ n_pts,
     assemble_hband(slab, L, n, nullptr, s_win);
     double *HB = slab + L.o_hb;
     for (int i = threadIdx.x; i < n; i += blockDim.x) HB[(size_t)i * HB_PITCH + HBW + 1] = 0.0;
-    if (threadIdx.x == 0) status[b] = 0;
+    if (threadIdx.x == 0 && !s_flag) status[b] = 0;
+}
+
+// followers of a shared centreline: copy what the owner assembled (vectors V_H .. V_KREF, V_F, V_IH and the band of H)
+__global__ void __launch_bounds__(256)
+mincurv_share_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, const int32_t *__restrict__ centre_id,
+                     double *__restrict__ ws, Layout L, int32_t *__restrict__ status) {
+    const int b = blockIdx.x;
+    const int o = centre_id[b];
+    if (o == b) return;
+    const int n = n_pts ? n_pts[b] : n_max;
+    if (n < N_MIN || n > n_max) return;                       // (status -1 from the assembly kernel)
+    if (o < 0 || o >= B || centre_id[o] != o || (n_pts ? n_pts[o] : n_max) != n) {
+        if (threadIdx.x == 0) status[b] = -1;                 // not a valid owner
+        return;
+    }
+    const double *src = ws + (size_t)o * L.stride;
+    double *dst = ws + (size_t)b * L.stride;
+    const size_t np = (size_t)L.np;
+    auto copy = [&](size_t off, size_t count) {               // (all offsets and counts are multiples of 2 doubles)
+        const double2 *s2 = reinterpret_cast<const double2 *>(src + off);
+        double2 *d2 = reinterpret_cast<double2 *>(dst + off);
+        for (size_t i = threadIdx.x; i < count / 2; i += blockDim.x) d2[i] = s2[i];
+    };
+    copy((size_t)V_H * np, (size_t)(V_KREF - V_H + 1) * np);
+    copy((size_t)V_F * np, np);
+    copy((size_t)V_IH * np, np);
+    copy(L.o_hb, np * HB_PITCH);
 }
 
 void launch_mincurv_setup(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
-                          const double *h, double w_veh, const double *w_veh_batch, double f_scale, double *ws,
-                          const Layout &L, int32_t *status, cudaStream_t stream) {
+                          const double *h, double w_veh, const double *w_veh_batch, double f_scale, const int32_t *centre_id,
+                          double *ws, const Layout &L, int32_t *status, cudaStream_t stream) {
     constexpr int smem = hband_win_doubles(256) * (int)sizeof(double);      // 49 KB: above the static limit
     // (per launch: the attribute is per device and a process may drive several)
     cudaFuncSetAttribute(mincurv_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    mincurv_setup_kernel<<<B, 256, smem, stream>>>(n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, f_scale, ws, L, status);
+    mincurv_setup_kernel<<<B, 256, smem, stream>>>(n_max, n_pts, reftrack, normvec, h, w_veh, w_veh_batch, f_scale, centre_id, ws, L,
+                                                   status);
+    if (centre_id) mincurv_share_kernel<<<B, 256, 0, stream>>>(B, n_max, n_pts, centre_id, ws, L, status);
 }
 
 }  // namespace mc

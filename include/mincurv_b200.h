@@ -104,6 +104,25 @@ int mc_mincurv_solve_batch_ex(int B, int n_max, const int32_t *n_pts,
                               int32_t *status, int32_t *iters,
                               void *workspace, size_t workspace_bytes, void *stream);
 
+/* the same for batches in which several instances share a centreline (x, y, normal vectors, h and n_pts identical, only
+ * the track widths / vehicle width differ -- e.g. the width variants of one track, /root/reference/main_globaltraj.py:264-271
+ * called in a sweep): H, f and k_ref depend on the centreline only, so they are assembled once per centreline and copied.
+ *   centre_id [B] or NULL : centre_id[b] = index (in this batch) of the instance that owns b's centreline; owners have
+ *                           centre_id[b] == b.  NULL: every instance is assembled on its own.  A follower whose owner is
+ *                           not an owner itself, is out of range or has another n_pts gets status -1.
+ * The results are identical to the unshared call (the shared quantities are bitwise the same). */
+int mc_mincurv_solve_batch_shared(int B, int n_max, const int32_t *n_pts,
+                                  const double *reftrack, const double *normvec, const double *h,
+                                  double kappa_bound, double w_veh, const double *w_veh_batch, double f_scale,
+                                  const int32_t *centre_id,
+                                  double *alpha, double *curv_error_max, double *kappa_lin_max,
+                                  int32_t *status, int32_t *iters,
+                                  void *workspace, size_t workspace_bytes, void *stream);
+int mc_mincurv_setup_batch_shared(int B, int n_max, const int32_t *n_pts, const double *reftrack, const double *normvec,
+                                  const double *h, double w_veh, const double *w_veh_batch, double f_scale,
+                                  const int32_t *centre_id, int32_t *status,
+                                  void *workspace, size_t workspace_bytes, void *stream);
+
 /* The three stages of mc_mincurv_solve_batch as separate stream-ordered calls on the same workspace
  * (assembly of the banded QP, interior-point solve, post-solve curvature check / linearisation error);
  * mc_mincurv_solve_batch is exactly setup -> pdip -> finalize.  Exposed so that a caller can time or

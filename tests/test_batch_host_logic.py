@@ -53,7 +53,7 @@ def test_every_wrapper_matches_the_signature_table(fake):
     npts = torch.full((B,), n, dtype=torch.int32)
     cx, cy, nv, h = B_.calc_splines_batch(rt, n_pts=npts)
     res = B_.opt_min_curv_batch(rt, nv, h, 0.12, torch.full((B,), 2.0, dtype=torch.float64), n_pts=npts)
-    assert _names(fake).count("mc_mincurv_solve_batch_ex") == 3                     # 5 tracks in chunks of 2
+    assert _names(fake).count("mc_mincurv_solve_batch_shared") == 3                     # 5 tracks in chunks of 2
     assert res["alpha"].shape == (B, n)
     alpha = torch.zeros((B, n), dtype=torch.float64)      # (the stand-in library writes nothing: outputs are uninitialised)
     B_.opt_shortest_path_batch(rt, nv, 2.0, n_pts=npts)
@@ -88,9 +88,31 @@ def test_every_wrapper_matches_the_signature_table(fake):
     assert smoothed.shape[0] == B and smoothed.shape[2] == 4 and n_smoothed.shape == (B,) and lam.shape == (B,)
     used = set(_names(fake))
     assert used >= set(_lib.EXPORTED_SYMBOLS) - {"mc_version", "mc_last_error", "mc_debug_read_profile", "mc_debug_factor_solve",
-                                                 "mc_mincurv_setup_batch", "mc_mincurv_setup_batch_ex", "mc_mincurv_solve_batch",
+                                                 "mc_mincurv_setup_batch", "mc_mincurv_setup_batch_ex", "mc_mincurv_setup_batch_shared",
+                                                 "mc_mincurv_solve_batch", "mc_mincurv_solve_batch_ex",
                                                  "mc_vel_profile_batch", "mc_mincurv_pdip_batch", "mc_mincurv_finalize_batch",
                                                  "mc_mincurv_kappa_batch", "mc_iqp_finish_batch", "mc_jitter_widths_batch"}
+
+
+def test_shared_centre_ids_and_their_chunking(fake, monkeypatch):
+    """centre_id: owners are the first instance of every group; inside a chunk the first instance of the chunk with the
+    same owner takes the role (the owner itself may live in another chunk)."""
+    group = torch.tensor([7, 3, 7, 3, 3, 9], dtype=torch.int64)
+    cid = B_.shared_centre_ids(group)
+    assert cid.dtype == torch.int32 and cid.tolist() == [0, 1, 0, 1, 1, 5]
+    B, n = 6, 120
+    rt = torch.rand((B, n, 4), dtype=torch.float64) + 3.0
+    cx, cy, nv, h = B_.calc_splines_batch(rt)
+    fake.calls.clear()
+    local, real = [], B_.shared_centre_ids
+    monkeypatch.setattr(B_, "shared_centre_ids", lambda g: local.append(real(g)) or local[-1])
+    B_.opt_min_curv_batch(rt, nv, h, 0.12, 2.0, centre_id=cid)           # the fixture forces chunks of 3
+    calls = [c[1] for c in fake.calls if c[0] == "mc_mincurv_solve_batch_shared"]
+    assert [c[0] for c in calls] == [3, 3]
+    assert [t.tolist() for t in local] == [[0, 1, 0], [0, 0, 2]]           # local owners of [0, 1, 0] and [1, 1, 5]
+    assert [c[10].value for c in calls] == [t.data_ptr() for t in local]
+    with pytest.raises(ValueError, match="centre_id"):
+        B_.opt_min_curv_batch(rt, nv, h, 0.12, 2.0, centre_id=cid[:4])
 
 
 def test_launches_with_the_track_index_on_grid_y_are_chunked(fake, monkeypatch):
@@ -114,7 +136,7 @@ def test_globaltraj_batch_wires_the_stages_in_the_reference_order(fake, opt_type
     mach = np.array([[0.0, 5.0], [80.0, 5.0]])
     out = globaltraj.globaltraj_batch(rt, opt_type, globaltraj.default_pars(), ggv, mach)
     order = [nm for nm in _names(fake) if not nm.endswith("_workspace_bytes")]
-    qp = "mc_mincurv_solve_batch_ex" if opt_type == "mincurv" else "mc_shortest_path_solve_batch"
+    qp = "mc_mincurv_solve_batch_shared" if opt_type == "mincurv" else "mc_shortest_path_solve_batch"
     want = ["mc_calc_splines_batch", qp, "mc_create_raceline_batch", "mc_vel_profile_batch_ex", "mc_assemble_trajectory_batch",
             "mc_interp_track_batch", "mc_min_bound_dists_batch", "mc_traj_extrema_batch"]
     staged = [nm for nm in order if nm in want]                   # (helper launches such as mc_polygon_length_batch aside)
@@ -135,13 +157,13 @@ def test_iqp_batch_grows_its_buffers_when_a_resampled_track_does_not_fit(fake, m
 
     def patched(self, name):
         fn = real_getattr(self, name)
-        if name == "mc_mincurv_solve_batch_ex":
+        if name == "mc_mincurv_solve_batch_shared":
             def solve(*a):
                 fn(*a)
                 bq, nmax = a[0], a[1]
-                ctypes.memset(a[10].value, 0, bq * nmax * 8)                     # alpha = 0
-                ctypes.memset(a[11].value, 0, bq * 8)                            # curv_error_max = 0 (converged once iter >= iters_min)
-                ctypes.memset(a[13].value, 0, bq * 4)                            # status = 0
+                ctypes.memset(a[11].value, 0, bq * nmax * 8)                     # alpha = 0
+                ctypes.memset(a[12].value, 0, bq * 8)                            # curv_error_max = 0 (converged once iter >= iters_min)
+                ctypes.memset(a[14].value, 0, bq * 4)                            # status = 0
                 return 0
             return solve
         if name == "mc_iqp_finish_batch":

@@ -192,3 +192,31 @@ def test_device_generated_variants_match_the_host_mirror():
     # default centre assignment: variant v uses track v % n_base
     out2, _ = B_.jitter_widths_batch(torch.tensor(base, device=dev), torch.tensor(seeds[:3]))
     assert np.array_equal(out2.cpu().numpy(), out[:3])
+
+
+@pytest.mark.gpu
+def test_shared_centre_lines_give_the_same_results_as_the_unshared_call():
+    """Width variants of one track share H, f and k_ref: with centre_id the assembly runs once per centre line and is
+    copied (mc_mincurv_solve_batch_shared).  The results must be bitwise those of the unshared call; a follower that
+    points at a non-owner is refused with status -1."""
+    dev = torch.device("cuda")
+    n, n_base, V = 400, 3, 14
+    base = synth.make_batch(4242, n_base, n)
+    rts = np.stack([base[v % n_base] if v < n_base else synth.jitter_widths(base[v % n_base], 99 + v) for v in range(V)])
+    rt = torch.tensor(rts, device=dev)
+    cx, cy, nv, h = B_.calc_splines_batch(rt)
+    w_veh = torch.linspace(1.8, 2.6, V, dtype=torch.float64, device=dev)
+    ref = B_.opt_min_curv_batch(rt, nv, h, 0.12, w_veh)
+    cid = B_.shared_centre_ids(torch.arange(V, device=dev) % n_base)
+    assert cid.tolist() == [v % n_base for v in range(V)]
+    got = B_.opt_min_curv_batch(rt, nv, h, 0.12, w_veh, centre_id=cid)
+    assert torch.equal(got["status"], ref["status"]) and int((ref["status"] == 0).sum()) == V
+    assert torch.equal(got["alpha"], ref["alpha"]) and torch.equal(got["curv_error_max"], ref["curv_error_max"])
+    # chunked: the owner of a chunk is its first instance with that centre line
+    got2 = B_.opt_min_curv_batch(rt, nv, h, 0.12, w_veh, centre_id=cid, max_chunk=5)
+    assert torch.equal(got2["alpha"], ref["alpha"])
+    bad = cid.clone()
+    bad[7] = 4                     # instance 4 is a follower itself
+    got3 = B_.opt_min_curv_batch(rt, nv, h, 0.12, w_veh, centre_id=bad)
+    st = got3["status"].tolist()
+    assert st[7] == -1 and all(s == 0 for i, s in enumerate(st) if i != 7)
