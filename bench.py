@@ -61,19 +61,21 @@ def make_inputs(batch: int, n: int, seed0: int) -> np.ndarray:
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons of one GPU during the timed region (pynvml)."""
+    """Samples SM clock / throttle reasons of one GPU during the timed region (pynvml).  NVML is initialised in the
+    constructor, i.e. BEFORE the timed region: nvmlInit inside the sampling thread took driver locks while the first timed
+    steps were being launched (a step of 28 ms measured as 42 ms on some boxes)."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
         self._halt = threading.Event()
-
-    def run(self):
+        self._nv = None
         try:
             import pynvml
             pynvml.nvmlInit()
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+
             def const(new, old):
                 return getattr(pynvml, new, None) or getattr(pynvml, old)
             names = {const("nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"): "hw_slowdown",
@@ -82,6 +84,17 @@ class ClockSampler(threading.Thread):
                      const("nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"): "sw_power_cap"}
             get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
                 getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)          # first query outside the timed region too
+            get_reasons(h)
+            self._nv = (pynvml, h, names, get_reasons)
+        except Exception as e:  # clocks are evidence, not a dependency of the measurement
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def run(self):
+        if self._nv is None:
+            return
+        pynvml, h, names, get_reasons = self._nv
+        try:
             while not self._halt.is_set():
                 self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 r = get_reasons(h)
@@ -89,7 +102,7 @@ class ClockSampler(threading.Thread):
                     if r & bit:
                         self.reasons.add(nm)
                 time.sleep(0.02)
-        except Exception as e:  # clocks are evidence, not a dependency of the measurement
+        except Exception as e:
             self.reasons.add(f"sampler_error:{type(e).__name__}")
 
     def stop(self) -> dict:
@@ -317,9 +330,12 @@ def run_b200(args) -> dict:
     tm.on = True
     t0.record()
     res = None
+    marks = [t0]
     for _ in range(args.steps):
         res = step(rt, tm)
         collect(res)                                     # gather of step k overlaps the kernels of step k + 1
+        marks.append(torch.cuda.Event(enable_timing=True))
+        marks[-1].record()
     if gather is not None and gather._pending:
         gathered = gather.finish()                       # (the last gather ends inside the timed region)
     t1.record()
@@ -327,6 +343,7 @@ def run_b200(args) -> dict:
     sync_all()
     clocks = sampler.stop()
     ms_local = t0.elapsed_time(t1)
+    step_ms = [round(marks[i].elapsed_time(marks[i + 1]), 3) for i in range(len(marks) - 1)]
     tmax = torch.tensor([ms_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -403,7 +420,8 @@ def run_b200(args) -> dict:
     iters_mean = float(res["iters"].double().mean().item()) if "iters" in res else None
     line = {
         "metric": METRIC if cfg == "c1" else f"QPs/sec, BASELINE.json config {cfg}", "value": qps, "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "step_ms": step_ms,
+        "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"batch {bl} per GPU: " + CONFIGS[cfg]["what"] + f", N={n} points",
                    "baseline_config": cfg, "global_batch": total, "n_points": n, "kappa_bound": KAPPA_BOUND,

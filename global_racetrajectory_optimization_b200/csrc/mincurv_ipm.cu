@@ -952,7 +952,7 @@ mincurv_pdip_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, double 
         }
         gmax = block_reduce<1>(gmax, sh.red);
         fmaxv = block_reduce<1>(fmaxv, sh.red);
-        const double lam0 = 1e-2 * gmax + 1e-300;
+        const double lam0 = prm.lam0_rel * gmax + 1e-300;
         double musum = 0.0;
 #pragma unroll 1
         for (int i = threadIdx.x; i < n; i += IP_THREADS) {
@@ -1249,7 +1249,7 @@ mincurv_pdip_kappa_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, d
         }
         gmax = block_reduce<1>(gmax, sh.red);
         fmaxv = block_reduce<1>(fmaxv, sh.red);
-        const double lam0 = 1e-2 * gmax + 1e-300;
+        const double lam0 = prm.lam0_rel * gmax + 1e-300;
         double musum = 0.0;
         for (int i = threadIdx.x; i < n; i += IP_THREADS) {
             const double gi = ETV[i] + F[i];

@@ -52,6 +52,7 @@ struct PdipParams {
     double rd_rel;     // ... and |r_d|_inf <= rd_rel * (|f|_inf + |g0|_inf)
     double eta;        // fraction to the boundary
     double dx_rel;     // ... and the last step moved alpha by <= dx_rel * max(|alpha|_inf, 0.01 m)  (0: not checked)
+    double lam0_rel;   // initial multipliers: max(-+g, 0) + lam0_rel * |g|_inf
 };
 
 __device__ __forceinline__ double *vec(double *slab, const Layout &L, int v) { return slab + (size_t)v * L.np; }

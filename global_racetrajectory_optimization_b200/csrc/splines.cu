@@ -18,19 +18,72 @@ __host__ __device__ inline int spl_np(int n_max) { return ((n_max + 31) / 32) * 
 size_t spline_ws_doubles(int n_max) { return (size_t)S_NUM * spl_np(n_max); }
 
 // ---------------------------------------------------------------------------------------------
-// Closed spline through (PX, PY) with parameter scales H: moments by the periodic tridiagonal LDL^T of common.cuh's
-// scheme (every thread runs the recurrences over a chunk of TRI_CHUNK points after a warm-up of TRI_WARM points), here on
-// EIGHT vectors that live in shared memory whenever the track fits (n_max <= ~3400 points): H, PX, PY (inputs), INVD,
-// Y0, Y1, MX, MY.  Diagonal, sub-diagonal factors and right-hand sides are formed on the fly from H / PX / PY instead of
-// being staged through further vectors.  (The first version kept fifteen scratch vectors per track in global memory:
-// 127 KB per track, 300 MB for the bench batch -- 6.9 % of the HBM roofline.)
+// Closed spline through (PX, PY) with parameter scales H on EIGHT vectors that live in shared memory whenever the track
+// fits (n_max <= ~3400 points): H, PX, PY (inputs) and the five vectors of the periodic tridiagonal moment system
+//   h_{i-1} m_{i-1} + 2 (h_{i-1} + h_i) m_i + h_i m_{i+1} = 6 ((p_{i+1} - p_i) / h_i - (p_i - p_{i-1}) / h_{i-1}).
+// Tracks of up to 2048 points: PARALLEL CYCLIC REDUCTION, in place -- at stride s every equation eliminates its neighbours
+// i - s and i + s with their own equations; the off-diagonal / diagonal ratio is squared by every step (diagonal dominance:
+// <= 1/2 to start with), so after six steps (stride 64) the couplings are below 1e-17 of the diagonal and m = r / b.  All
+// threads work on all points in every step (no serial recurrence, one reciprocal per point and step).  Longer tracks use
+// the chunked LDL^T recurrences (every thread runs a chunk of TRI_CHUNK points after a warm-up of TRI_WARM points).
+// (The first version kept fifteen scratch vectors per track in global memory -- 6.9 % of the HBM roofline; the second
+// ran the chunked recurrences for every track: 64 dependent steps with divisions per thread, 3.7 %.)
 // ---------------------------------------------------------------------------------------------
 constexpr int SPL_SM_VECS = 8;
 __host__ __device__ inline size_t spline_smem_bytes(int n_max) { return (size_t)SPL_SM_VECS * spl_np(n_max) * sizeof(double); }
 constexpr size_t SPL_SMEM_LIMIT = 220 * 1024;
 
-__device__ void closed_spline(double *sm, int np, int n, double *__restrict__ cx, double *__restrict__ cy,
-                              double *__restrict__ nvec) {
+__device__ __forceinline__ double spl_rcp(double d) {      // 1 / d for a positive normal d (seed + two Newton steps)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(r, fma(-d, r, 1.0), r);
+    return fma(r, fma(-d, r, 1.0), r);
+}
+
+// moments MX, MY (vectors 6, 7) by parallel cyclic reduction; EPT = points per thread (n <= EPT * blockDim.x).
+// The equations are kept normalised (diagonal 1): a_i m_{i-s} + m_i + c_i m_{i+s} = r_i, so a step costs one reciprocal.
+template <int EPT>
+__device__ void spline_moments_pcr(double *sm, int np, int n) {
+    const double *H = sm, *PX = sm + np, *PY = sm + 2 * np;
+    double *A = sm + 3 * np, *C = sm + 5 * np, *RX = sm + 6 * np, *RY = sm + 7 * np;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int im1 = (i == 0) ? n - 1 : i - 1, ip1 = (i + 1 == n) ? 0 : i + 1;
+        const double hi = H[i], hm = H[im1];
+        const double ih = spl_rcp(hi), ihm = spl_rcp(hm), w = 6.0 * spl_rcp(2.0 * (hm + hi));
+        const double px = PX[i], py = PY[i];
+        A[i] = hm * w * (1.0 / 6.0); C[i] = hi * w * (1.0 / 6.0);
+        RX[i] = w * ((PX[ip1] - px) * ih - (px - PX[im1]) * ihm);
+        RY[i] = w * ((PY[ip1] - py) * ih - (py - PY[im1]) * ihm);
+    }
+    __syncthreads();
+    for (int s = 1; s < 64; s <<= 1) {
+        double na[EPT], nc[EPT], nx[EPT], ny[EPT];
+        const int st = s % n;                                   // (tiny tracks: the stride wraps)
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const int i = threadIdx.x + e * blockDim.x;
+            if (i < n) {
+                int im = i - st; if (im < 0) im += n;
+                int ip = i + st; if (ip >= n) ip -= n;
+                const double k1 = A[i], k2 = C[i];
+                const double w = spl_rcp(fma(-C[im], k1, fma(-A[ip], k2, 1.0)));
+                na[e] = -A[im] * k1 * w;
+                nc[e] = -C[ip] * k2 * w;
+                nx[e] = fma(-RX[im], k1, fma(-RX[ip], k2, RX[i])) * w;
+                ny[e] = fma(-RY[im], k1, fma(-RY[ip], k2, RY[i])) * w;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const int i = threadIdx.x + e * blockDim.x;
+            if (i < n) { A[i] = na[e]; C[i] = nc[e]; RX[i] = nx[e]; RY[i] = ny[e]; }
+        }
+        __syncthreads();
+    }
+}
+
+__device__ void spline_moments_chunked(double *sm, int np, int n) {
     const double *H = sm, *PX = sm + np, *PY = sm + 2 * np;
     double *INVD = sm + 3 * np, *Y0 = sm + 4 * np, *Y1 = sm + 5 * np, *MX = sm + 6 * np, *MY = sm + 7 * np;
     // ---- forward pivots d_i = 2 (h_{i-1} + h_i) - h_{i-1}^2 / d_{i-1}; stored as 1 / d_i ----
@@ -94,6 +147,15 @@ __device__ void closed_spline(double *sm, int np, int n, double *__restrict__ cx
         }
     }
     __syncthreads();
+}
+
+__device__ void closed_spline(double *sm, int np, int n, double *__restrict__ cx, double *__restrict__ cy,
+                              double *__restrict__ nvec) {
+    const double *H = sm, *PX = sm + np, *PY = sm + 2 * np;
+    const double *MX = sm + 6 * np, *MY = sm + 7 * np;
+    if (n <= 4 * (int)blockDim.x) spline_moments_pcr<4>(sm, np, n);
+    else if (n <= 8 * (int)blockDim.x) spline_moments_pcr<8>(sm, np, n);
+    else spline_moments_chunked(sm, np, n);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int ip1 = (i + 1 == n) ? 0 : i + 1;
         const double h2 = H[i] * H[i];
