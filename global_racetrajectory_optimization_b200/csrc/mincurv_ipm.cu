@@ -69,6 +69,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 #ifndef MC_WAIT_MODE
 #define MC_WAIT_MODE 1
 #endif
+
 // MC_WAIT_MODE 0: try_wait with a long suspend hint (the thread is parked until the phase completes);
 //              1: test_wait spin (non-blocking probe): the waiter resumes within a few cycles of the arrival.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
@@ -80,20 +81,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
                  " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 #endif
 }
-// same, for the warp that is normally AHEAD of its producer (the fill warp): back off between probes so that the
-// probes do not take issue slots from the chain warps of the same scheduler
+// same, for the warp that is normally AHEAD of its producer (the fill warp, ~20 % of its time): parked by the hardware
+// (try_wait with a suspend hint) instead of probing -- the probes of the spin version were 16 % of all executed instructions
+// and took issue slots from the chain warps of the same scheduler; runs with them fell into a slow mode now and then.
+// -DMC_RELAXED_SPIN_NS=<ns> restores the probing loop with that back-off, for experiments.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, unsigned parity) {
-#if MC_WAIT_MODE == 0
-    mbar_wait(bar, parity);
+#ifndef MC_RELAXED_SPIN_NS
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"
+                 " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 #else
     unsigned ok = 0;
     for (;;) {
         asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (ok) break;
-#ifndef MC_EXP_SPIN
-        __nanosleep(20);
-#endif
+        __nanosleep(MC_RELAXED_SPIN_NS);
     }
 #endif
 }
