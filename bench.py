@@ -95,13 +95,16 @@ class ClockSampler(threading.Thread):
             return
         pynvml, h, names, get_reasons = self._nv
         try:
+            # a few samples per timed region, not a tight poll: NVML queries take driver locks that the launching thread
+            # needs too (sporadic ~100 ms gaps between launches were seen with a 20 ms poll)
+            time.sleep(0.01)
             while not self._halt.is_set():
                 self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 r = get_reasons(h)
                 for bit, nm in names.items():
                     if r & bit:
                         self.reasons.add(nm)
-                time.sleep(0.02)
+                self._halt.wait(0.05)
         except Exception as e:
             self.reasons.add(f"sampler_error:{type(e).__name__}")
 
@@ -325,25 +328,31 @@ def run_b200(args) -> dict:
         gather.finish()
     sync_all()
     sampler = ClockSampler(local_rank)
+    import gc
+    gc.collect()
+    gc.disable()                                         # no collector pauses between launches inside the timed region
     sampler.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tm.on = True
     t0.record()
     res = None
-    marks = [t0]
+    marks, host_marks = [t0], [time.perf_counter()]
     for _ in range(args.steps):
         res = step(rt, tm)
         collect(res)                                     # gather of step k overlaps the kernels of step k + 1
         marks.append(torch.cuda.Event(enable_timing=True))
         marks[-1].record()
+        host_marks.append(time.perf_counter())           # (launch-side time of the step: a gap here is a host stall)
     if gather is not None and gather._pending:
         gathered = gather.finish()                       # (the last gather ends inside the timed region)
     t1.record()
     tm.on = False
     sync_all()
+    gc.enable()
     clocks = sampler.stop()
     ms_local = t0.elapsed_time(t1)
     step_ms = [round(marks[i].elapsed_time(marks[i + 1]), 3) for i in range(len(marks) - 1)]
+    host_step_ms = [round(1e3 * (host_marks[i + 1] - host_marks[i]), 3) for i in range(len(host_marks) - 1)]
     tmax = torch.tensor([ms_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -420,7 +429,7 @@ def run_b200(args) -> dict:
     iters_mean = float(res["iters"].double().mean().item()) if "iters" in res else None
     line = {
         "metric": METRIC if cfg == "c1" else f"QPs/sec, BASELINE.json config {cfg}", "value": qps, "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "step_ms": step_ms,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "step_ms": step_ms, "host_launch_ms": host_step_ms,
         "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"batch {bl} per GPU: " + CONFIGS[cfg]["what"] + f", N={n} points",
