@@ -322,8 +322,12 @@ def run_b200(args) -> dict:
             gather.start(res["alpha"][:, :n].contiguous() if res["alpha"].shape[1] != n else res["alpha"], res["status"])
 
     # ---- device-resident measurement ("value") ----
+    res = None
     for _ in range(args.warmup):
-        collect(step(rt, tm))
+        res = step(rt, tm)                               # (the previous step's results stay alive while the next one runs,
+        collect(res)                                     #  exactly as in the timed loop: the allocator's cache then holds both
+                                                         #  sets of output buffers -- a cold second set cost one cudaMalloc burst
+                                                         #  of ~100 ms inside the timed region in some runs)
     if gather is not None and gather._pending:
         gather.finish()
     sync_all()
@@ -576,7 +580,9 @@ def run_e2e(args, W, torch, B_, dev, world, sync_all, dist) -> dict:
                 oh[key].copy_(src, non_blocking=True)
                 src.record_stream(d2h)
 
-    for phase_steps in (min(args.warmup, 2), args.steps):
+    # warm-up: enough steps for the allocator's cache to hold every buffer set that is alive at once in steady state (outputs
+    # handed to the copy stream are recycled one step later than those of the compute stream)
+    for phase_steps in (max(args.warmup, 4), args.steps):
         nsteps = phase_steps
         for e in ev_free:
             e.record(cur)
