@@ -220,14 +220,14 @@ def build_workload(cfg_name, args, dev, rank, torch, B_, lib, _lib):
                 _lib.check(lib.mc_mincurv_pdip_batch(Bq, n, None, p(alpha), p(st), p(iters), p(ws), ws.numel(), s), "pdip")
             _lib.check(lib.mc_mincurv_finalize_batch(Bq, n, None, p(alpha), KAPPA_BOUND, p(cerr), p(kmax), p(st), p(ws), ws.numel(), s), "finalize")
             # curvature-row phase for the instances the box-only phase flagged (none on this workload: the kernel scans
-            # the status words and returns) + re-evaluation -- together the five launches of mc_mincurv_solve_batch
+            # the status words and returns) + re-evaluation -- together the six launches of mc_mincurv_solve_batch_shared
             _lib.check(lib.mc_mincurv_kappa_batch(Bq, n, None, KAPPA_BOUND, p(alpha), p(st), p(iters), p(ws), ws.numel(), s), "kappa")
             _lib.check(lib.mc_mincurv_finalize_batch(Bq, n, None, p(alpha), KAPPA_BOUND, p(cerr), p(kmax), p(st), p(ws), ws.numel(), s), "finalize")
             with tm.span("raceline"):
                 rl = B_.create_raceline_batch(rt_dev, nv, alpha, STEP_INTERP, n_out_max=n_out_max, with_head_curv=True)
             return dict(alpha=alpha, status=st, iters=iters, kappa=rl["kappa"], raceline=rl["raceline_interp"],
                         n_out=rl["n_out"], el=rl["el_lengths_interp"])
-        W.update(step=step, qps_per_step=bl, launches=7)
+        W.update(step=step, qps_per_step=bl, launches=8)       # splines, setup, share, pdip, finalize, kappa, finalize, raceline
 
     elif cfg_name == "c3":
         def step(rt_dev, tm):
