@@ -69,6 +69,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 #ifndef MC_WAIT_MODE
 #define MC_WAIT_MODE 1
 #endif
+#ifndef MC_RELAXED_BACKOFF_NS
+#define MC_RELAXED_BACKOFF_NS 250
+#endif
 
 // MC_WAIT_MODE 0: try_wait with a long suspend hint (the thread is parked until the phase completes);
 //              1: test_wait spin (non-blocking probe): the waiter resumes within a few cycles of the arrival.
@@ -87,8 +90,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 // -DMC_RELAXED_SPIN_NS=<ns> restores the probing loop with that back-off, for experiments.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, unsigned parity) {
 #ifndef MC_RELAXED_SPIN_NS
-    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"
-                 " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+    // (one try_wait parks the warp for well under a microsecond before it reports "not yet": the back-off between two
+    //  of them keeps the probes of a ~1400-cycle wait at a handful instead of ~200)
+    unsigned ok = 0;
+    for (;;) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(MC_RELAXED_BACKOFF_NS);
+    }
 #else
     unsigned ok = 0;
     for (;;) {
@@ -103,20 +113,10 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, unsigned parity
 // keep for 1184 resident instances): its copies and stores carry an evict-first L2 policy so that they do not push the
 // O(N) iterate vectors of the interior-point loop out of L2.
 template <typename T>
-__device__ __forceinline__ void st_stream(T *p, T v) {
-#ifdef MC_EXP_NOSTCS
-    *p = v;
-#else
-    __stcs(p, v);
-#endif
-}
+__device__ __forceinline__ void st_stream(T *p, T v) { __stcs(p, v); }      // factor rows: streaming (evict-first) stores
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     uint64_t pol;
-#ifdef MC_EXP_EVICT_NORMAL
-    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
-#else
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-#endif
     return pol;
 }
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar, uint64_t policy) {
@@ -160,9 +160,6 @@ __device__ __forceinline__ double fast_rcp(double d) {
 }
 // x with its high word ANDed with m (m = 0: a denormal of magnitude < 2^-1022, i.e. zero for every purpose here;
 // m = ~0: x).  One LOP3 instead of a 64-bit select: resets the accumulators of the lane whose row enters the window.
-__device__ __forceinline__ double mask_hi(double x, int m) {
-    return __hiloint2double(__double2hiint(x) & m, __double2loint(x));
-}
 
 // one panel (eight columns) handed from warp 0 to warp 1
 struct Handoff {
@@ -562,24 +559,23 @@ __device__ __noinline__ bool factor(IpShared &sh, double *slab, const Layout &L,
                 }
             }
         __syncwarp();
-        // right-looking LDL^T with this lane's row in registers (full square, like the chain: no masks)
+        // right-looking LDL^T in place in shared memory, lane = row (the full square is kept up to date, so row k is also
+        // column k).  A loop, not 32 unrolled steps on a register row: that version was 51 KB of SASS run once per
+        // factorisation (same speed, a quarter of the kernel's instruction footprint).
         bool ok = true;
-        double row[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) row[c] = sh.s.Ss[lane * 33 + c];
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < 32; ++k) {
-            double *cb = sh.part[k & 1];
-            cb[lane] = row[k];
-            __syncwarp();
-            const double d = cb[k];
+            const double d = sh.s.Ss[k * 33 + k];
             if (!(d > 0.0)) ok = false;
             const double w = fast_rcp(d);
-            const double l = row[k] * w;
-#pragma unroll
-            for (int c = k + 1; c < 32; ++c) row[c] = fma(-l, cb[c], row[c]);
-            if (lane > k) sh.s.Ss[lane * 33 + k] = l;
+            const double l = sh.s.Ss[lane * 33 + k] * w;
+            if (lane > k) {
+#pragma unroll 4
+                for (int c = k + 1; c < 32; ++c) sh.s.Ss[lane * 33 + c] = fma(-l, sh.s.Ss[k * 33 + c], sh.s.Ss[lane * 33 + c]);
+                sh.s.Ss[lane * 33 + k] = l;
+            }
             if (lane == k) sh.wS[k] = w;
+            __syncwarp();
         }
         if (!ok) sh.flag = 1;
     }
@@ -626,9 +622,12 @@ __device__ __forceinline__ int prog_read(const int *p) {
     return v;
 }
 // wait until *p >= need (bounded: a protocol error must not hang the device; it is reported like a failed pivot)
+template <bool BACKOFF = false>
 __device__ __forceinline__ void prog_wait(IpShared &sh, const int *p, int need) {
-    for (int spin = 0; spin < (1 << 18); ++spin)
+    for (int spin = 0; spin < (1 << 18); ++spin) {
         if (prog_read(p) >= need) return;
+        if (BACKOFF) __nanosleep(MC_RELAXED_BACKOFF_NS);      // warp 1's waits: it is the one with slack in both sweeps
+    }
     sh.flag = 1;
 }
 
@@ -717,7 +716,7 @@ __device__ __noinline__ void sweep_sep_rhs(IpShared &sh, const double *__restric
     int sl = 0, sn = AHEAD % GT_SLOTS;
     for (int u = 0; u < nunits; ++u, sl = (sl == GT_SLOTS - 1) ? 0 : sl + 1, sn = (sn == GT_SLOTS - 1) ? 0 : sn + 1) {
         const double *gt = R.wait(sl) + lane;
-        prog_wait(sh, &sh.prog[0], u + 1);
+        prog_wait<true>(sh, &sh.prog[0], u + 1);
         const double *zq = &sh.u.sw.q[(u & (QDEPTH - 1)) * SUB];       // (padding columns: z = 0, g = 0)
 #pragma unroll
         for (int s2 = 0; s2 < SUB; s2 += 2) {
@@ -767,7 +766,7 @@ __device__ __noinline__ void sweep_sep_solve(IpShared &sh, const double *__restr
     int sl = 0, sn = AHEAD % GT_SLOTS;
     for (int i = 0; i < nunits; ++i, sl = (sl == GT_SLOTS - 1) ? 0 : sl + 1, sn = (sn == GT_SLOTS - 1) ? 0 : sn + 1) {
         const int k = (U0 - i) * SUB + kl;
-        if ((i & 7) == 0 && i >= 8) prog_wait(sh, &sh.prog[2], i - 8);      // queue slots of the next eight units are free again
+        if ((i & 7) == 0 && i >= 8) prog_wait<true>(sh, &sh.prog[2], i - 8);      // queue slots of the next eight units are free again
         const double *gt = R.wait(sl) + kl * FROW;
         const double2 zw = *reinterpret_cast<const double2 *>(&gt[32]);
         double c0 = 0.0, c1 = 0.0;
@@ -1225,7 +1224,6 @@ mincurv_pdip_kappa_kernel(int B, int n_max, const int32_t *__restrict__ n_pts, d
         const int n = n_pts ? n_pts[b] : n_max;
         double *aout = alpha_out + (size_t)b * n_max;
         double *slab = ws + (size_t)b * L.stride;
-        const double *HB = slab + L.o_hb;
         const double *__restrict__ LB = vec(slab, L, V_LB), *__restrict__ UB = vec(slab, L, V_UB), *__restrict__ F = vec(slab, L, V_F);
         const double *__restrict__ KR = vec(slab, L, V_KREF);
         double *__restrict__ AL = vec(slab, L, V_ALPHA), *__restrict__ LU = vec(slab, L, V_LU), *__restrict__ LL = vec(slab, L, V_LL);
