@@ -4,7 +4,8 @@
 //   [NUM_VEC][np]        O(N) vectors (geometry, linearisation, interior-point iterates)
 //   [n_max][ZB_PITCH]    bands of B_t = Ti diag(w_t) Ti, t = 0..2  (assembly scratch, mincurv_setup.cu)
 //   [np][HB_PITCH]       band of H = E^T E              (row i: H[i][i .. i+32], cyclic)
-//   2 x [np][34]         bordered LDL^T factor of H + D: unit-lower columns L, fill columns G (mincurv_ipm.cu)
+//   [np][42] + [np][34]  bordered LDL^T factor of H + D: chain rows [Q - I | L21 | - | w] per panel of eight columns,
+//                        fill rows [G | z | w] (mincurv_ipm.cu)
 #pragma once
 #include "common.cuh"
 

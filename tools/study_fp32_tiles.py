@@ -2,7 +2,7 @@
 solve in fp32 (half the HBM and shared-memory traffic of the triangular sweeps) and let the interior-point iteration,
 whose residuals stay fp64, absorb the inexact Newton directions.
 
-CPU emulation (numpy): the same block-cyclic factorisation as csrc/mincurv_pdip.cu (32 x 32 chain blocks, 32-row
+CPU emulation (numpy): the block-cyclic factorisation of round 1's csrc/mincurv_pdip.cu (replaced by csrc/mincurv_ipm.cu in round 2) (32 x 32 chain blocks, 32-row
 separator, explicit Linv tiles, T and F tiles) computed in fp64, then every stored tile rounded to fp32 before the
 sweeps use it; Mehrotra predictor-corrector on the banded QP of the fixtures.  Reports iterations and the error of alpha
 against the all-fp64 run and against the dense oracle.
