@@ -385,7 +385,7 @@ def scale_alpha_batch(alpha: torch.Tensor, scale: Union[float, torch.Tensor]) ->
 def iqp_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, kappa_bound: float,
               w_veh: Union[float, torch.Tensor], stepsize_interp: float, iters_min: int = 3,
               curv_error_allowed: float = 0.01, n_pts: Optional[torch.Tensor] = None, max_iters: int = 50,
-              fixed_iters: Optional[int] = None) -> dict:
+              fixed_iters: Optional[int] = None, _n_cap_min: int = 0) -> dict:
     """Batched tph.iqp_handler: per-instance outer iterations with damping and
     re-linearisation; an instance leaves the loop once iter >= iters_min and its curv_error_max <=
     curv_error_allowed.  Returns dict(alpha [B, n_cap], reftrack [B, n_cap, 4], normvec [B, n_cap, 2],
@@ -393,8 +393,12 @@ def iqp_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, ka
     status: the QP status of that iteration, or 2 if max_iters outer iterations did not reach curv_error_allowed (tph
     would keep iterating).  One small device->host read per outer iteration.
 
-    fixed_iters: run exactly that many outer iterations for every instance (bench config C3)."""
+    fixed_iters: run exactly that many outer iterations for every instance (bench config C3).  Nothing has to be decided
+    on the host between the iterations then, so they are queued back to back and the one thing the host would have
+    looked at -- a re-sampled track that does not fit the capacity -- is checked once at the end (and the call repeated
+    with the larger capacity, which the 5 % + 50 m of slack makes a rare event)."""
     _require_cuda()
+    reftrack0, normvec0, h0 = reftrack, normvec, h           # (the caller's arrays: never written)
     reftrack = _f64(reftrack, "reftrack").clone()
     normvec = _f64(normvec, "normvec").clone()
     h = _f64(h, "h").clone()
@@ -406,7 +410,7 @@ def iqp_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, ka
     # follows from its length, not from n_max (a track given at a coarser spacing grows); 5 % + 50 m of slack on the
     # reference polygon, and the relinearisation step below grows the buffers if a track still does not fit
     poly = float(_closed_polygon_length(reftrack, cur_n).max().item())
-    n_cap = max(n_max + 64, int(math.ceil((1.05 * poly + 50.0) / float(stepsize_interp))) + 16)
+    n_cap = max(n_max + 64, int(math.ceil((1.05 * poly + 50.0) / float(stepsize_interp))) + 16, int(_n_cap_min))
 
     def _alloc(cap):
         return dict(alpha=torch.zeros((B, cap), dtype=torch.float64, device=dev),
@@ -425,6 +429,7 @@ def iqp_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, ka
     qp_solves = 0
     it = 0
     limit = fixed_iters if fixed_iters is not None else max_iters
+    worst = None              # fixed_iters: smallest new point count seen so far (device scalar; negative = overflow)
     while True:
         it += 1
         n_cur_max = reftrack.shape[1]
@@ -443,6 +448,13 @@ def iqp_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, ka
         _lib.check(rc, "mc_iqp_finish_batch")
         if it >= limit:                       # every track was finished by this call (fixed count or cap): nothing to read back
             break
+        if fixed_iters is not None:
+            rt_new, nv_new, n_new = iqp_relinearise_batch(reftrack, normvec, alpha, stepsize_interp, n_pts=cur_n,
+                                                          active=active, n_max_new=n_cap)
+            worst = n_new.min() if worst is None else torch.minimum(worst, n_new.min())
+            reftrack, normvec, cur_n = rt_new, nv_new, n_new
+            h = torch.ones((B, n_cap), dtype=torch.float64, device=dev)
+            continue
         while True:
             rt_new, nv_new, n_new = iqp_relinearise_batch(reftrack, normvec, alpha, stepsize_interp, n_pts=cur_n,
                                                           active=active, n_max_new=n_cap)
@@ -460,6 +472,12 @@ def iqp_batch(reftrack: torch.Tensor, normvec: torch.Tensor, h: torch.Tensor, ka
             break
         reftrack, normvec, cur_n = rt_new, nv_new, n_new
         h = torch.ones((B, n_cap), dtype=torch.float64, device=dev)   # use_dist_scaling=False from iteration 2 on
+    if worst is not None:
+        n_min = int(worst.item())
+        if n_min < 0:         # a re-sampled track did not fit: its later iterations ran on nothing -- repeat with room for it
+            return iqp_batch(reftrack0, normvec0, h0, kappa_bound, w_veh, stepsize_interp, iters_min=iters_min,
+                             curv_error_allowed=curv_error_allowed, n_pts=n_pts, max_iters=max_iters,
+                             fixed_iters=fixed_iters, _n_cap_min=-n_min + 64)
     fin["qp_solves"] = qp_solves
     return fin
 

@@ -206,3 +206,36 @@ def test_iqp_batch_grows_its_buffers_when_a_resampled_track_does_not_fit(fake, m
     cap = state["caps"][1]
     assert res["alpha"].shape == (B, cap) and res["reftrack"].shape == (B, cap, 4) and res["normvec"].shape == (B, cap, 2)
     assert res["outer_iters"].tolist() == [2, 2] and res["n_pts"].tolist() == [cap - 5, cap - 5] and res["qp_solves"] == 4
+
+
+def test_iqp_batch_with_a_fixed_iteration_count_checks_the_capacity_once_at_the_end(fake, monkeypatch):
+    """fixed_iters: the iterations are queued without host reads; an overflow reported by mc_iqp_relinearise_batch in any of
+    them makes the call repeat once with room for the largest track."""
+    import ctypes
+    B, n = 2, 100
+    state = {"caps": []}
+    real_getattr = FakeLib.__getattr__
+
+    def patched(self, name):
+        fn = real_getattr(self, name)
+        if name != "mc_iqp_relinearise_batch":
+            return fn
+
+        def relin(*a):
+            fn(*a)
+            cap = a[8]
+            state["caps"].append(cap)
+            need = -(cap + 30) if len(state["caps"]) == 2 else cap - 5          # the second re-sampling of the first pass overflows
+            ctypes.memmove(a[11].value, (ctypes.c_int32 * B)(*([need] * B)), 4 * B)
+            return 0
+        return relin
+    monkeypatch.setattr(FakeLib, "__getattr__", patched)
+    rt = torch.rand((B, n, 4), dtype=torch.float64) + 3.0
+    nv = torch.rand((B, n, 2), dtype=torch.float64)
+    h = torch.ones((B, n), dtype=torch.float64)
+    res = B_.iqp_batch(rt, nv, h, 0.12, 2.0, 3.0, fixed_iters=4)
+    first = state["caps"][0]
+    # 3 re-samplings per pass (4 iterations), two passes; the second pass runs with the capacity the overflow asked for
+    assert len(state["caps"]) == 6 and state["caps"][:3] == [first] * 3 and state["caps"][3:] == [first + 30 + 64] * 3
+    assert res["alpha"].shape == (B, first + 30 + 64) and res["qp_solves"] == 4 * B
+    assert _names(fake).count("mc_mincurv_solve_batch_shared") == 2 * 4 * 2        # (the fixture forces chunks of one track)
