@@ -23,7 +23,8 @@ size_t spline_ws_doubles(int n_max) { return (size_t)S_NUM * spl_np(n_max); }
 //   h_{i-1} m_{i-1} + 2 (h_{i-1} + h_i) m_i + h_i m_{i+1} = 6 ((p_{i+1} - p_i) / h_i - (p_i - p_{i-1}) / h_{i-1}).
 // Tracks of up to 2048 points: PARALLEL CYCLIC REDUCTION, in place -- at stride s every equation eliminates its neighbours
 // i - s and i + s with their own equations; the off-diagonal / diagonal ratio is squared by every step (diagonal dominance:
-// <= 1/2 to start with), so after six steps (stride 64) the couplings are below 1e-17 of the diagonal and m = r / b.  All
+// <= 1/2 to start with), so after six steps (stride 64; five for uniform scales) the couplings are below 1e-17 of the
+// diagonal and m = r / b.  All
 // threads work on all points in every step (no serial recurrence, one reciprocal per point and step).  Longer tracks use
 // the chunked LDL^T recurrences (every thread runs a chunk of TRI_CHUNK points after a warm-up of TRI_WARM points).
 // (The first version kept fifteen scratch vectors per track in global memory -- 6.9 % of the HBM roofline; the second
@@ -43,7 +44,7 @@ __device__ __forceinline__ double spl_rcp(double d) {      // 1 / d for a positi
 // moments MX, MY (vectors 6, 7) by parallel cyclic reduction; EPT = points per thread (n <= EPT * blockDim.x).
 // The equations are kept normalised (diagonal 1): a_i m_{i-s} + m_i + c_i m_{i+s} = r_i, so a step costs one reciprocal.
 template <int EPT>
-__device__ void spline_moments_pcr(double *sm, int np, int n) {
+__device__ void spline_moments_pcr(double *sm, int np, int n, int s_end) {
     const double *H = sm, *PX = sm + np, *PY = sm + 2 * np;
     double *A = sm + 3 * np, *C = sm + 5 * np, *RX = sm + 6 * np, *RY = sm + 7 * np;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -56,7 +57,7 @@ __device__ void spline_moments_pcr(double *sm, int np, int n) {
         RY[i] = w * ((PY[ip1] - py) * ih - (py - PY[im1]) * ihm);
     }
     __syncthreads();
-    for (int s = 1; s < 64; s <<= 1) {
+    for (int s = 1; s < s_end; s <<= 1) {
         double na[EPT], nc[EPT], nx[EPT], ny[EPT];
         const int st = s % n;                                   // (tiny tracks: the stride wraps)
 #pragma unroll
@@ -149,12 +150,16 @@ __device__ void spline_moments_chunked(double *sm, int np, int n) {
     __syncthreads();
 }
 
+// uniform: all parameter scales equal (H = 1: create_raceline, calc_splines without distance scaling) -- the couplings start
+// at 1/4 of the diagonal and fall to 5e-19 after FIVE steps (0.25 -> 0.071 -> 5.2e-3 -> 2.7e-5 -> 7.3e-10 -> 5.3e-19);
+// scaled spacings start anywhere below 1/2 and get the sixth step.
 __device__ void closed_spline(double *sm, int np, int n, double *__restrict__ cx, double *__restrict__ cy,
-                              double *__restrict__ nvec) {
+                              double *__restrict__ nvec, bool uniform) {
     const double *H = sm, *PX = sm + np, *PY = sm + 2 * np;
     const double *MX = sm + 6 * np, *MY = sm + 7 * np;
-    if (n <= 4 * (int)blockDim.x) spline_moments_pcr<4>(sm, np, n);
-    else if (n <= 8 * (int)blockDim.x) spline_moments_pcr<8>(sm, np, n);
+    const int s_end = uniform ? 32 : 64;
+    if (n <= 4 * (int)blockDim.x) spline_moments_pcr<4>(sm, np, n, s_end);
+    else if (n <= 8 * (int)blockDim.x) spline_moments_pcr<8>(sm, np, n, s_end);
     else spline_moments_chunked(sm, np, n);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int ip1 = (i + 1 == n) ? 0 : i + 1;
@@ -205,7 +210,7 @@ calc_splines_kernel(int n_max, const int32_t *__restrict__ n_pts, const double *
     __syncthreads();
     closed_spline(sv, np, n, coeffs_x ? coeffs_x + (size_t)b * n_max * 4 : nullptr,
                   coeffs_y ? coeffs_y + (size_t)b * n_max * 4 : nullptr,
-                  normvec ? normvec + (size_t)b * n_max * 2 : nullptr);
+                  normvec ? normvec + (size_t)b * n_max * 2 : nullptr, !use_dist_scaling);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -265,7 +270,7 @@ create_raceline_kernel(int n_max, const int32_t *__restrict__ n_pts, const doubl
         H[i] = 1.0;
     }
     __syncthreads();
-    closed_spline(sv, np, n, cx, cy, nullptr);
+    closed_spline(sv, np, n, cx, cy, nullptr, true);
     // spline lengths: polyline through 15 equidistant t samples (tph.calc_spline_lengths, no_interp_points=15)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const double4 a = *reinterpret_cast<const double4 *>(cx + (size_t)i * 4);
